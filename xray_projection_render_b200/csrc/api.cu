@@ -1,0 +1,789 @@
+// api.cu -- C-ABI entry points of libcuda_render.so (see include/xray_cuda_render.h).
+//
+// Host orchestration around the kernels: scene upload (cached per device), fp64 sample-lattice
+// tables, camera preparation, view batching with pinned double-buffered D2H, modulo view
+// sharding over several GPUs (one host thread per device, volume replicated over NVLink P2P),
+// and the three legacy symbols of the reference plugin (cuda_backend.h).
+//
+// Contract kept from the reference plugin (cuda_backend.cu:82-203): synchronous unless the
+// *Device* variant is used, 0 on success, small positive codes on failure, never exit/abort,
+// nothing printed to stdout, callable from any OS thread (device set explicitly per call).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/xray_cuda_render.h"
+#include "device_types.h"
+#include "scene.h"
+
+namespace xr {
+cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream);
+cudaError_t launch_voxelize_scene(const RenderParams& P, int res, float* d_out, cudaStream_t stream);
+cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream);
+cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
+                                      const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
+cudaError_t measure_fp32_peak(double* tflops);
+}  // namespace xr
+
+using namespace xr;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+static int fail_cuda(int code, const char* what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear sticky-less errors
+    return code;
+}
+#define CU(code, call)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return fail_cuda(code, #call, e__); \
+    } while (0)
+
+static const double kCubeHalfDiagonal = 1.74;  // main.go:46
+
+// ---------------------------------------------------------------------------------------
+// Device-side scene cache
+// ---------------------------------------------------------------------------------------
+struct DevScene {
+    int dev = -1;
+    unsigned char* d_blob = nullptr;
+    VoxelDev* d_vox_table = nullptr;
+    void* d_vox[kMaxVoxelSlots] = {nullptr};
+    size_t vox_bytes[kMaxVoxelSlots] = {0};
+    uint64_t vox_version[kMaxVoxelSlots] = {0};
+    bool vox_borrowed[kMaxVoxelSlots] = {false};
+};
+struct SceneCache {
+    std::mutex mu;
+    std::map<int, DevScene> per_dev;
+};
+
+static SceneCache* cache_of(XRayScene* sc) {
+    if (!sc->device_cache) sc->device_cache = new SceneCache();
+    return (SceneCache*)sc->device_cache;
+}
+
+static void free_dev_scene(DevScene& ds) {
+    if (ds.dev < 0) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(ds.dev);
+    if (ds.d_blob) cudaFree(ds.d_blob);
+    if (ds.d_vox_table) cudaFree(ds.d_vox_table);
+    for (int s = 0; s < kMaxVoxelSlots; ++s)
+        if (ds.d_vox[s] && !ds.vox_borrowed[s]) cudaFree(ds.d_vox[s]);
+    cudaSetDevice(cur);
+    ds = DevScene();
+}
+
+// Upload (or reuse) the program and voxel data on the current device.
+// borrowed_vox: optional device pointer to use for slot 0 instead of host data.
+static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const void* borrowed_vox, DevScene** out) {
+    SceneCache* c = cache_of(sc);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DevScene& ds = c->per_dev[dev];
+    const Header* h = (const Header*)sc->blob.data();
+    if (ds.dev < 0) {
+        ds.dev = dev;
+        CU(3, cudaMalloc(&ds.d_blob, sc->blob.size()));
+        CU(4, cudaMemcpyAsync(ds.d_blob, sc->blob.data(), sc->blob.size(), cudaMemcpyHostToDevice, stream));
+        CU(3, cudaMalloc(&ds.d_vox_table, sizeof(VoxelDev) * kMaxVoxelSlots));
+    }
+    VoxelDev table[kMaxVoxelSlots] = {};
+    for (int s = 0; s < (int)h->n_voxel_slots; ++s) {
+        VoxelHost& vh = sc->vox[s];
+        table[s].nx = vh.nx;
+        table[s].ny = vh.ny;
+        table[s].nz = vh.nz;
+        table[s].dtype = vh.dtype;
+        if (s == 0 && borrowed_vox) {
+            if (ds.d_vox[0] && !ds.vox_borrowed[0]) cudaFree(ds.d_vox[0]);
+            ds.d_vox[0] = const_cast<void*>(borrowed_vox);
+            ds.vox_borrowed[0] = true;
+            table[0].dtype = 0;
+        } else if (vh.data) {
+            size_t bytes = (size_t)vh.nx * vh.ny * vh.nz * (vh.dtype == 0 ? 4 : 8);
+            if (ds.vox_version[s] != vh.version || ds.vox_bytes[s] != bytes || ds.vox_borrowed[s]) {
+                if (ds.d_vox[s] && !ds.vox_borrowed[s] && ds.vox_bytes[s] != bytes) {
+                    cudaFree(ds.d_vox[s]);
+                    ds.d_vox[s] = nullptr;
+                }
+                if (ds.vox_borrowed[s]) ds.d_vox[s] = nullptr;
+                ds.vox_borrowed[s] = false;
+                if (!ds.d_vox[s]) CU(3, cudaMalloc(&ds.d_vox[s], bytes));
+                CU(4, cudaMemcpyAsync(ds.d_vox[s], vh.data, bytes, cudaMemcpyHostToDevice, stream));
+                ds.vox_bytes[s] = bytes;
+                ds.vox_version[s] = vh.version;
+            }
+        }
+        table[s].data = ds.d_vox[s];
+    }
+    CU(4, cudaMemcpyAsync(ds.d_vox_table, table, sizeof(table), cudaMemcpyHostToDevice, stream));
+    CU(4, cudaStreamSynchronize(stream));  // table[] is a stack temporary
+    *out = &ds;
+    return 0;
+}
+
+static void fill_scene_dev(const XRayScene* sc, const DevScene& ds, SceneDev& sd) {
+    const Header* h = (const Header*)sc->blob.data();
+    sd.instr = (const Instr*)(ds.d_blob + h->instr_off);
+    sd.f32 = (const float4*)(ds.d_blob + h->f32_off);
+    sd.f64 = (const double*)(ds.d_blob + h->f64_off);
+    sd.grids = (const unsigned long long*)(ds.d_blob + h->grid_off);
+    sd.deform = (const DeformRec*)(ds.d_blob + h->deform_off);
+    sd.n_instr = (int)h->n_instr;
+    sd.n_deform = (int)h->n_deform;
+    sd.f32_count = (int)h->f32_count;
+    sd.save_depth = (int)h->save_depth;
+    sd.vox = ds.d_vox_table;
+}
+
+// ---------------------------------------------------------------------------------------
+// fp64 sample lattice (main.go:147 `s += ds`, :176-196 `right += DS`), built by repeated addition.
+// ---------------------------------------------------------------------------------------
+static void build_lattice(int integrator, double ds, double smin, double smax, std::vector<double>& s_tab) {
+    s_tab.clear();
+    if (integrator == XRAY_INTEGRATE_SIMPLE) {
+        for (double s = smin; s < smax; s += ds) s_tab.push_back(s);
+    } else {
+        s_tab.push_back(smin);  // left of the first interval
+        for (double right = smin + ds; right <= smax; right += ds) s_tab.push_back(right);
+    }
+}
+
+static double focal_from_fov(double fov_deg) { return 1 / std::tan((fov_deg / 2) * M_PI / 180.0); }  // main.go:457
+
+// ---------------------------------------------------------------------------------------
+// One device's share of a render
+// ---------------------------------------------------------------------------------------
+struct Job {
+    XRayScene* scene;
+    const XRayCameraParams64* cams;
+    std::vector<int> views;  // indices into cams / output, all with the same R
+    int res;
+    XRayRenderOpts opts;
+    double ds;
+    void* out;          // host or device base pointer of the full output
+    bool out_on_device;
+    int dev;
+    cudaStream_t user_stream;
+    bool use_user_stream;
+    const void* borrowed_vox;
+    bool fast_volume;  // dedicated voxel kernel (single voxel_grid root, fp32, simple, no warp)
+    unsigned long long stats[XRAY_NUM_STATS];
+    int rc;
+    std::string err;
+};
+
+static int run_job(Job& J) {
+    cudaError_t e;
+    CU(3, cudaSetDevice(J.dev));
+    cudaStream_t stream = J.user_stream;
+    bool own_stream = false;
+    if (!J.use_user_stream) {
+        CU(3, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    int rc = 0;
+    const int nv = (int)J.views.size();
+    const int res = J.res;
+    const size_t esz = J.opts.out_dtype == XRAY_OUT_F64 ? 8 : 4;
+    const size_t img_bytes = (size_t)res * res * esz;
+    CamDev* d_cams = nullptr;
+    double* d_s = nullptr;
+    float* d_t = nullptr;
+    unsigned long long* d_stats = nullptr;
+    unsigned char* d_img[2] = {nullptr, nullptr};
+    unsigned char* h_pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::vector<CamDev> hc(nv);
+    std::vector<double> s_tab;
+    std::vector<float> t_tab;
+    DevScene* ds = nullptr;
+    RenderParams P = {};
+
+    auto cleanup = [&]() {
+        if (d_cams) cudaFree(d_cams);
+        if (d_s) cudaFree(d_s);
+        if (d_t) cudaFree(d_t);
+        if (d_stats) cudaFree(d_stats);
+        for (int b = 0; b < 2; ++b) {
+            if (d_img[b]) cudaFree(d_img[b]);
+            if (h_pin[b]) cudaFreeHost(h_pin[b]);
+            if (ev[b]) cudaEventDestroy(ev[b]);
+        }
+        if (own_stream) cudaStreamDestroy(stream);
+    };
+#define CUJ(code, call)                               \
+    do {                                              \
+        e = (call);                                   \
+        if (e != cudaSuccess) {                       \
+            rc = fail_cuda(code, #call, e);           \
+            J.err = g_last_error;                     \
+            cleanup();                                \
+            return rc;                                \
+        }                                             \
+    } while (0)
+
+    if (nv == 0) {
+        cleanup();
+        return 0;
+    }
+    rc = ensure_dev_scene(J.scene, J.dev, stream, J.borrowed_vox, &ds);
+    if (rc) {
+        J.err = g_last_error;
+        cleanup();
+        return rc;
+    }
+    const Header* h = (const Header*)J.scene->blob.data();
+    fill_scene_dev(J.scene, *ds, P.scene);
+
+    const double R = J.cams[J.views[0]].R;
+    P.smin = R - kCubeHalfDiagonal;  // main.go:465
+    P.smax = R + kCubeHalfDiagonal;
+    P.s_center = R;
+    P.ds = J.ds;
+    P.ds_fine = J.ds / 10.0;  // main.go:178
+    build_lattice(J.opts.integration, J.ds, P.smin, P.smax, s_tab);
+    P.n_steps = J.opts.integration == XRAY_INTEGRATE_SIMPLE ? (int)s_tab.size() : (int)s_tab.size() - 1;
+    t_tab.resize(s_tab.size());
+    for (size_t k = 0; k < s_tab.size(); ++k) t_tab[k] = (float)(s_tab[k] - P.s_center);
+    for (int v = 0; v < nv; ++v) {
+        const XRayCameraParams64& c = J.cams[J.views[v]];
+        memcpy(hc[v].eye, c.eye, sizeof(c.eye));
+        memcpy(hc[v].view, c.view, sizeof(c.view));
+        hc[v].f = focal_from_fov(c.fov_y);
+    }
+    CUJ(3, cudaMalloc(&d_cams, sizeof(CamDev) * nv));
+    CUJ(4, cudaMemcpyAsync(d_cams, hc.data(), sizeof(CamDev) * nv, cudaMemcpyHostToDevice, stream));
+    CUJ(3, cudaMalloc(&d_s, sizeof(double) * std::max<size_t>(1, s_tab.size())));
+    CUJ(3, cudaMalloc(&d_t, sizeof(float) * std::max<size_t>(1, t_tab.size())));
+    if (!s_tab.empty()) {
+        CUJ(4, cudaMemcpyAsync(d_s, s_tab.data(), sizeof(double) * s_tab.size(), cudaMemcpyHostToDevice, stream));
+        CUJ(4, cudaMemcpyAsync(d_t, t_tab.data(), sizeof(float) * t_tab.size(), cudaMemcpyHostToDevice, stream));
+    }
+    if (J.opts.stats) {
+        CUJ(3, cudaMalloc(&d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS));
+        CUJ(4, cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * XRAY_NUM_STATS, stream));
+    }
+    P.s_tab = d_s;
+    P.t_tab = d_t;
+    P.res = res;
+    P.tiles_i = (res + kTileI - 1) / kTileI;
+    P.tiles_j = (res + kTileJ - 1) / kTileJ;
+    P.flat_field = J.opts.flat_field;
+    P.dm = J.opts.density_multiplier;
+    for (int a = 0; a < 3; ++a) {
+        P.aabb_lo[a] = h->aabb_lo[a];
+        P.aabb_hi[a] = h->aabb_hi[a];
+    }
+    P.out_f64 = J.opts.out_dtype == XRAY_OUT_F64;
+    P.stats = d_stats;
+    {
+        size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
+        size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));
+        size_t queue = (size_t)kQueueCap * kBlockThreads * sizeof(int);
+        P.prog_in_smem = (prog + stack + queue) <= 160 * 1024 ? 1 : 0;
+        P.smem_prog_bytes = P.prog_in_smem ? (unsigned int)prog : 0u;
+    }
+
+    // Contiguity: views of this job that are adjacent in the output can share one launch.
+    // Batch = run of views; device-resident output renders straight into place when the views
+    // are consecutive, otherwise view by view.
+    const size_t max_batch_bytes = (size_t)256 << 20;
+    int max_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nv, max_batch_bytes / img_bytes));
+    auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
+        P.cams = d_cams + v0;
+        P.n_views = n;
+        P.out = d_dst;
+        // the grid is one CTA per (view, tile); keep it below 2^31
+        if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
+        if (J.fast_volume)
+            return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
+                                             h->voxel_dims[0][2], P, stream);
+        return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
+    };
+
+    if (J.out_on_device) {
+        int v = 0;
+        while (v < nv) {
+            int n = 1;
+            while (v + n < nv && n < max_batch && J.views[v + n] == J.views[v + n - 1] + 1) ++n;
+            CUJ(5, launch(v, n, (unsigned char*)J.out + (size_t)J.views[v] * img_bytes));
+            v += n;
+        }
+    } else {
+        cudaPointerAttributes attr;
+        bool out_pinned = cudaPointerGetAttributes(&attr, J.out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        for (int b = 0; b < 2; ++b) {
+            CUJ(3, cudaMalloc(&d_img[b], (size_t)max_batch * img_bytes));
+            if (!out_pinned) CUJ(3, cudaMallocHost(&h_pin[b], (size_t)max_batch * img_bytes));
+            CUJ(3, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+        }
+        int pend_v0[2] = {0, 0}, pend_n[2] = {0, 0};
+        auto drain = [&](int b) -> cudaError_t {  // copy batch b from pinned staging into the caller's buffer
+            if (pend_n[b] == 0) return cudaSuccess;
+            cudaError_t ee = cudaEventSynchronize(ev[b]);
+            if (ee != cudaSuccess) return ee;
+            if (!out_pinned)
+                for (int k = 0; k < pend_n[b]; ++k)
+                    memcpy((unsigned char*)J.out + (size_t)J.views[pend_v0[b] + k] * img_bytes, h_pin[b] + (size_t)k * img_bytes,
+                           img_bytes);
+            pend_n[b] = 0;
+            return cudaSuccess;
+        };
+        int v = 0, b = 0;
+        while (v < nv) {
+            int n = std::min(max_batch, nv - v);
+            CUJ(7, drain(b));  // buffer b is free again once its previous batch reached the caller
+            CUJ(5, launch(v, n, d_img[b]));
+            if (out_pinned) {
+                for (int k = 0; k < n; ++k)
+                    CUJ(8, cudaMemcpyAsync((unsigned char*)J.out + (size_t)J.views[v + k] * img_bytes,
+                                           d_img[b] + (size_t)k * img_bytes, img_bytes, cudaMemcpyDeviceToHost, stream));
+            } else {
+                CUJ(8, cudaMemcpyAsync(h_pin[b], d_img[b], (size_t)n * img_bytes, cudaMemcpyDeviceToHost, stream));
+            }
+            CUJ(7, cudaEventRecord(ev[b], stream));
+            pend_v0[b] = v;
+            pend_n[b] = n;
+            v += n;
+            b ^= 1;
+        }
+        CUJ(7, drain(b));
+        CUJ(7, drain(b ^ 1));
+    }
+    if (J.opts.stats) {
+        CUJ(8, cudaMemcpyAsync(J.stats, d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS, cudaMemcpyDeviceToHost, stream));
+        CUJ(7, cudaStreamSynchronize(stream));
+    } else if (!J.out_on_device) {
+        CUJ(7, cudaStreamSynchronize(stream));
+    }
+    if (J.out_on_device && !J.use_user_stream) CUJ(7, cudaStreamSynchronize(stream));
+    if (J.out_on_device && J.use_user_stream) {
+        // scratch (cams, tables) is freed below: cudaFree synchronises with outstanding work on
+        // the device, so the asynchronous contract holds for the caller-visible buffers only
+        // after this point; keep the cost off the hot path by retiring scratch via the stream.
+        CUJ(7, cudaStreamSynchronize(stream));
+    }
+    cleanup();
+    return 0;
+#undef CUJ
+}
+
+static int resolve_ds(const XRayScene* sc, double ds_in, double& ds) {
+    const Header* h = (const Header*)sc->blob.data();
+    ds = ds_in > 0 ? ds_in : h->min_feature_size / 5.0;  // main.go:350-353
+    if (!(ds > 0) || !std::isfinite(ds)) return fail(2, "step size ds is not positive/finite (scene has no finite MinFeatureSize?)");
+    if (3.48 / ds > 5.0e7) return fail(2, "step size ds too small for the sample-lattice table");
+    return 0;
+}
+
+static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n, int res, const XRayRenderOpts* opts_in,
+                         void* out, bool out_on_device, const void* borrowed_vox, bool fast_volume) {
+    if (!scene || !cams || !out) return fail(1, "null pointer argument");
+    if (n <= 0 || res <= 0) return fail(2, "num_cameras and image_res must be positive");
+    XRayRenderOpts opts;
+    if (opts_in) {
+        if (opts_in->struct_size != sizeof(XRayRenderOpts)) return fail(2, "XRayRenderOpts.struct_size mismatch");
+        opts = *opts_in;
+    } else {
+        XRayRenderOptsInit(&opts);
+    }
+    if (opts.integration != XRAY_INTEGRATE_SIMPLE && opts.integration != XRAY_INTEGRATE_HIERARCHICAL)
+        return fail(2, "unknown integration mode");
+    if (opts.precision != XRAY_PRECISION_FP32 && opts.precision != XRAY_PRECISION_FP64) return fail(2, "unknown precision");
+    if (opts.out_dtype != XRAY_OUT_F32 && opts.out_dtype != XRAY_OUT_F64) return fail(2, "unknown out_dtype");
+    const Header* h = (const Header*)scene->blob.data();
+    for (int s = 0; s < (int)h->n_voxel_slots; ++s)
+        if (!scene->vox[s].data && !(s == 0 && borrowed_vox)) return fail(2, "voxel_grid slot has no data (XRaySceneSetVoxelData)");
+    double ds;
+    if (int rc = resolve_ds(scene, opts.ds, ds)) return rc;
+
+    std::vector<int> devs;
+    if (out_on_device || opts.num_devices <= 0) {
+        int cur = 0;
+        CU(3, cudaGetDevice(&cur));
+        devs.push_back(cur);
+    } else {
+        int count = 0;
+        CU(3, cudaGetDeviceCount(&count));
+        if (opts.num_devices > XRAY_MAX_DEVICES) return fail(2, "too many devices");
+        for (int i = 0; i < opts.num_devices; ++i) {
+            if (opts.devices[i] < 0 || opts.devices[i] >= count) return fail(2, "device index out of range");
+            devs.push_back(opts.devices[i]);
+        }
+    }
+    const int G = (int)devs.size();
+
+    // group views by R (the sample lattice depends on R), then shard each group modulo G
+    std::vector<double> Rs;
+    for (int v = 0; v < n; ++v)
+        if (std::find(Rs.begin(), Rs.end(), cams[v].R) == Rs.end()) Rs.push_back(cams[v].R);
+    unsigned long long stats_total[XRAY_NUM_STATS] = {0};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    for (double R : Rs) {
+        std::vector<Job> jobs(G);
+        for (int g = 0; g < G; ++g) {
+            Job& J = jobs[g];
+            J.scene = scene;
+            J.cams = cams;
+            J.res = res;
+            J.opts = opts;
+            J.ds = ds;
+            J.out = out;
+            J.out_on_device = out_on_device;
+            J.dev = devs[g];
+            J.user_stream = (cudaStream_t)(uintptr_t)opts.stream;
+            J.use_user_stream = out_on_device;
+            J.borrowed_vox = borrowed_vox;
+            J.fast_volume = fast_volume;
+            memset(J.stats, 0, sizeof(J.stats));
+            J.rc = 0;
+        }
+        int k = 0;
+        for (int v = 0; v < n; ++v)
+            if (cams[v].R == R) jobs[(k++) % G].views.push_back(v);  // v -> devices[v mod G], main.go:244
+        if (G == 1) {
+            jobs[0].rc = run_job(jobs[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; ++g) th.emplace_back([&jobs, g]() { jobs[g].rc = run_job(jobs[g]); });
+            for (auto& t : th) t.join();
+        }
+        cudaSetDevice(cur_dev);
+        for (int g = 0; g < G; ++g) {
+            if (jobs[g].rc) return fail(jobs[g].rc, jobs[g].err);
+            for (int s = 0; s < XRAY_NUM_STATS; ++s) stats_total[s] += jobs[g].stats[s];
+        }
+    }
+    if (opts.stats)
+        for (int s = 0; s < XRAY_NUM_STATS; ++s) opts.stats[s] += stats_total[s];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Extended C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char* XRayLastError(void) { return g_last_error.c_str(); }
+
+int XRayDeviceCount(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void XRayRenderOptsInit(XRayRenderOpts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->struct_size = sizeof(XRayRenderOpts);
+    o->integration = XRAY_INTEGRATE_HIERARCHICAL;  // reference default, main.go:39
+    o->precision = XRAY_PRECISION_FP32;
+    o->out_dtype = XRAY_OUT_F32;
+    o->ds = -1.0;
+    o->flat_field = 0.0;
+    o->density_multiplier = 1.0;
+}
+
+int XRaySceneCompileJSON(const char* object_json, const char* deformation_json, XRayScene** out_scene) {
+    std::string err;
+    int rc = compile_scene_json(object_json, deformation_json, out_scene, err);
+    if (rc) return fail(rc, err);
+    return 0;
+}
+
+void XRaySceneFree(XRayScene* scene) {
+    if (!scene) return;
+    if (scene->device_cache) {
+        SceneCache* c = (SceneCache*)scene->device_cache;
+        for (auto& kv : c->per_dev) free_dev_scene(kv.second);
+        delete c;
+    }
+    delete scene;
+}
+
+double XRaySceneMinFeatureSize(const XRayScene* scene) {
+    return scene ? ((const Header*)scene->blob.data())->min_feature_size : 0.0;
+}
+
+const void* XRaySceneProgram(const XRayScene* scene, size_t* num_bytes) {
+    if (!scene) return nullptr;
+    if (num_bytes) *num_bytes = scene->blob.size();
+    return scene->blob.data();
+}
+
+void XRaySceneBounds(const XRayScene* scene, double* lo, double* hi) {
+    if (!scene) return;
+    const Header* h = (const Header*)scene->blob.data();
+    for (int a = 0; a < 3; ++a) {
+        if (lo) lo[a] = h->aabb_lo[a];
+        if (hi) hi[a] = h->aabb_hi[a];
+    }
+}
+
+int XRaySceneNumVoxelSlots(const XRayScene* scene) { return scene ? scene->n_vox : 0; }
+
+int XRaySceneVoxelDims(const XRayScene* scene, int slot, int* nx, int* ny, int* nz) {
+    if (!scene || slot < 0 || slot >= scene->n_vox) return fail(2, "voxel slot out of range");
+    if (nx) *nx = scene->vox[slot].nx;
+    if (ny) *ny = scene->vox[slot].ny;
+    if (nz) *nz = scene->vox[slot].nz;
+    return 0;
+}
+
+int XRaySceneSetVoxelData(XRayScene* scene, int slot, const void* data, int nx, int ny, int nz, int dtype) {
+    if (!scene || !data) return fail(1, "null pointer argument");
+    if (slot < 0 || slot >= scene->n_vox) return fail(2, "voxel slot out of range");
+    VoxelHost& v = scene->vox[slot];
+    if (nx != v.nx || ny != v.ny || nz != v.nz) return fail(2, "voxel data dimensions do not match the scene's resolution");
+    if (dtype != XRAY_VOXEL_F32 && dtype != XRAY_VOXEL_F64) return fail(2, "unknown voxel dtype");
+    v.data = data;
+    v.dtype = dtype;
+    v.version++;
+    return 0;
+}
+
+double XRaySceneDensityHost(const XRayScene* scene, double x, double y, double z, double density_multiplier) {
+    return scene ? host_density(*scene, x, y, z, density_multiplier) : 0.0;
+}
+
+int XRayCameraFromAngles(double azimuthal_deg, double polar_deg, double R, double fov_deg, XRayCameraParams64* out) {
+    if (!out) return fail(1, "null pointer argument");
+    camera_from_angles(azimuthal_deg, polar_deg, R, out->eye, out->view);
+    out->fov_y = fov_deg;
+    out->R = R;
+    return 0;
+}
+
+int XRayRenderSceneCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
+                        const XRayRenderOpts* opts, void* out_images) {
+    return render_common(scene, cameras, num_cameras, image_res, opts, out_images, false, nullptr, false);
+}
+
+int XRayRenderSceneDeviceCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
+                              const XRayRenderOpts* opts, void* d_out_images) {
+    return render_common(scene, cameras, num_cameras, image_res, opts, d_out_images, true, nullptr, false);
+}
+
+}  // extern "C"
+
+// A voxel_grid-rooted scene for the volume entry points.
+static int make_volume_scene(int nx, int ny, int nz, XRayScene** out) {
+    char json[160];
+    snprintf(json, sizeof(json), "{\"type\":\"voxel_grid\",\"resolution\":[%d,%d,%d]}", nx, ny, nz);
+    std::string err;
+    int rc = compile_scene_json(json, nullptr, out, err);
+    if (rc) return fail(rc, err);
+    return 0;
+}
+
+static bool volume_fast_path_ok(const XRayRenderOpts& o, int dtype) {
+    if (getenv("XRAY_VOLUME_GENERIC")) return false;
+    return dtype == XRAY_VOXEL_F32 && o.precision == XRAY_PRECISION_FP32 && o.integration == XRAY_INTEGRATE_SIMPLE;
+}
+
+extern "C" {
+
+int XRayRenderVolumeExCUDA(const void* volume, int volume_dtype, int nx, int ny, int nz, const XRayCameraParams64* cameras,
+                           int num_cameras, int image_res, const XRayRenderOpts* opts, void* out_images) {
+    if (!volume || !cameras || !out_images) return fail(1, "null pointer argument");
+    if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
+    XRayScene* sc = nullptr;
+    if (int rc = make_volume_scene(nx, ny, nz, &sc)) return rc;
+    int rc = XRaySceneSetVoxelData(sc, 0, volume, nx, ny, nz, volume_dtype);
+    XRayRenderOpts o;
+    if (opts) o = *opts;
+    else XRayRenderOptsInit(&o);
+    if (!rc) rc = render_common(sc, cameras, num_cameras, image_res, opts, out_images, false, nullptr,
+                                volume_fast_path_ok(o, volume_dtype));
+    std::string keep = g_last_error;
+    XRaySceneFree(sc);
+    g_last_error = keep;
+    return rc;
+}
+
+int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
+                               int num_cameras, int image_res, const XRayRenderOpts* opts, void* d_out_images) {
+    if (!d_volume || !cameras || !d_out_images) return fail(1, "null pointer argument");
+    if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
+    XRayScene* sc = nullptr;
+    if (int rc = make_volume_scene(nx, ny, nz, &sc)) return rc;
+    XRayRenderOpts o;
+    if (opts) o = *opts;
+    else XRayRenderOptsInit(&o);
+    int rc = render_common(sc, cameras, num_cameras, image_res, opts, d_out_images, true, d_volume,
+                           volume_fast_path_ok(o, XRAY_VOXEL_F32));
+    std::string keep = g_last_error;
+    XRaySceneFree(sc);
+    g_last_error = keep;
+    return rc;
+}
+
+int XRayVoxelizeSceneCUDA(XRayScene* scene, int res, double density_multiplier, float* out_volume) {
+    if (!scene || !out_volume) return fail(1, "null pointer argument");
+    if (res <= 0) return fail(2, "res must be positive");
+    int dev = 0;
+    CU(3, cudaGetDevice(&dev));
+    DevScene* ds = nullptr;
+    if (int rc = ensure_dev_scene(scene, dev, 0, nullptr, &ds)) return rc;
+    const Header* h = (const Header*)scene->blob.data();
+    RenderParams P = {};
+    fill_scene_dev(scene, *ds, P.scene);
+    P.dm = density_multiplier;
+    size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
+    P.prog_in_smem = prog <= 160 * 1024;
+    P.smem_prog_bytes = P.prog_in_smem ? (unsigned int)prog : 0u;
+    const size_t total = (size_t)res * res * res;
+    float* d_out = nullptr;
+    CU(3, cudaMalloc(&d_out, total * sizeof(float)));
+    cudaError_t e = launch_voxelize_scene(P, res, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out_volume, d_out, total * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail_cuda(5, "voxelize", e);
+    return 0;
+}
+
+int XRayMeasureFp32Peak(double* tflops) {
+    if (!tflops) return fail(1, "null pointer argument");
+    cudaError_t e = measure_fp32_peak(tflops);
+    if (e != cudaSuccess) return fail_cuda(5, "measure_fp32_peak", e);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Legacy plugin surface (reference cuda_backend.h)
+// ---------------------------------------------------------------------------------------
+
+// Devices for the legacy symbols: XRAY_CUDA_DEVICES="all" | "0,1,2" ; default = device 0
+// (the reference plugin never selects a device, i.e. implicit device 0).
+static void legacy_devices(XRayRenderOpts& o) {
+    o.num_devices = 1;
+    o.devices[0] = 0;
+    const char* e = getenv("XRAY_CUDA_DEVICES");
+    if (!e || !*e) return;
+    int count = XRayDeviceCount();
+    if (!strcmp(e, "all")) {
+        o.num_devices = std::max(1, std::min(count, XRAY_MAX_DEVICES));
+        for (int i = 0; i < o.num_devices; ++i) o.devices[i] = i;
+        return;
+    }
+    int n = 0;
+    const char* p = e;
+    while (*p && n < XRAY_MAX_DEVICES) {
+        char* end = nullptr;
+        long v = strtol(p, &end, 10);
+        if (end == p) break;
+        if (v >= 0 && v < count) o.devices[n++] = (int)v;
+        p = (*end == ',') ? end + 1 : end;
+    }
+    if (n > 0) o.num_devices = n;
+}
+
+int RenderVolumeProjectionsCUDA(const float* volume, int nx, int ny, int nz, const XRayCameraParams* cameras, int num_cameras,
+                                int image_res, float ds, float flat_field, float* out_images) {
+    if (!volume || !cameras || !out_images) return fail(1, "null pointer argument");  // cuda_backend.cu:95-97
+    if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
+    if (!(ds > 0.0f)) return fail(2, "ds must be positive");
+    // Everything crossing this boundary was narrowed to fp32 by the Go caller
+    // (cuda_backend.go:124-134,329-330); widen it back and integrate those exact values.
+    std::vector<XRayCameraParams64> cams(num_cameras);
+    for (int c = 0; c < num_cameras; ++c) {
+        for (int a = 0; a < 3; ++a) cams[c].eye[a] = (double)cameras[c].eye[a];
+        for (int a = 0; a < 16; ++a) cams[c].view[a] = (double)cameras[c].view[a];
+        cams[c].fov_y = (double)cameras[c].fov_y;
+        cams[c].R = (double)cameras[c].R;
+    }
+    XRayRenderOpts o;
+    XRayRenderOptsInit(&o);
+    o.integration = XRAY_INTEGRATE_SIMPLE;  // cuda_path.go:99 always takes the fixed-step integrator
+    o.precision = XRAY_PRECISION_FP32;
+    o.out_dtype = XRAY_OUT_F32;
+    o.ds = (double)ds;
+    o.flat_field = (double)flat_field;
+    o.density_multiplier = 1.0;
+    legacy_devices(o);
+    return XRayRenderVolumeExCUDA(volume, XRAY_VOXEL_F32, nx, ny, nz, cams.data(), num_cameras, image_res, &o, out_images);
+}
+
+static int assemble_common(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier, int grid_dim,
+                           const int* cell_offsets, const int* cyl_indices, int num_cyl_indices, float* out_volume) {
+    if (!cylinders || !out_volume) return fail(1, "null pointer argument");
+    if (num_cylinders <= 0 || res <= 0) return fail(2, "num_cylinders and res must be positive");
+    const size_t total = (size_t)res * res * res;
+    CU(3, cudaSetDevice(0));
+    CylinderParams* d_cyl = nullptr;
+    int *d_off = nullptr, *d_idx = nullptr;
+    float* d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    int rc = 0;
+    auto done = [&](int code, const char* what) {
+        if (e != cudaSuccess && !rc) rc = fail_cuda(code, what, e);
+        if (d_cyl) cudaFree(d_cyl);
+        if (d_off) cudaFree(d_off);
+        if (d_idx) cudaFree(d_idx);
+        if (d_out) cudaFree(d_out);
+        return rc;
+    };
+    if ((e = cudaMalloc(&d_cyl, sizeof(CylinderParams) * num_cylinders)) != cudaSuccess) return done(3, "cudaMalloc");
+    if ((e = cudaMalloc(&d_out, total * sizeof(float))) != cudaSuccess) return done(3, "cudaMalloc");
+    if ((e = cudaMemcpy(d_cyl, cylinders, sizeof(CylinderParams) * num_cylinders, cudaMemcpyHostToDevice)) != cudaSuccess)
+        return done(4, "cudaMemcpy");
+    if (grid_dim > 0) {
+        const size_t ncell = (size_t)grid_dim * grid_dim * grid_dim;
+        if ((e = cudaMalloc(&d_off, sizeof(int) * (ncell + 1))) != cudaSuccess) return done(3, "cudaMalloc");
+        if ((e = cudaMalloc(&d_idx, sizeof(int) * std::max(1, num_cyl_indices))) != cudaSuccess) return done(3, "cudaMalloc");
+        if ((e = cudaMemcpy(d_off, cell_offsets, sizeof(int) * (ncell + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return done(4, "cudaMemcpy");
+        if (num_cyl_indices > 0 &&
+            (e = cudaMemcpy(d_idx, cyl_indices, sizeof(int) * num_cyl_indices, cudaMemcpyHostToDevice)) != cudaSuccess)
+            return done(4, "cudaMemcpy");
+    }
+    e = launch_voxelize_cylinders(d_cyl, num_cylinders, res, density_multiplier, d_off, d_idx, grid_dim, d_out, 0);
+    if (e != cudaSuccess) return done(5, "voxelize kernel");
+    if ((e = cudaMemcpy(out_volume, d_out, total * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess)
+        return done(6, "cudaMemcpy D2H");
+    return done(0, "");
+}
+
+int AssembleVoxelGridCUDA(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier,
+                          float* out_volume) {
+    return assemble_common(cylinders, num_cylinders, res, density_multiplier, 0, nullptr, nullptr, 0, out_volume);
+}
+
+int AssembleVoxelGridSpatialCUDA(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier,
+                                 int grid_dim, const int* cell_offsets, const int* cyl_indices, int num_cyl_indices,
+                                 float* out_volume) {
+    if (!cell_offsets || (!cyl_indices && num_cyl_indices > 0)) return fail(1, "null pointer argument");
+    if (grid_dim <= 0 || num_cyl_indices < 0) return fail(2, "grid_dim must be positive");
+    // validate the caller's CSR before trusting it on the device
+    const size_t ncell = (size_t)grid_dim * grid_dim * grid_dim;
+    if (cell_offsets[0] != 0 || cell_offsets[ncell] != num_cyl_indices) return fail(2, "cell_offsets do not span cyl_indices");
+    for (size_t c = 0; c < ncell; ++c)
+        if (cell_offsets[c] > cell_offsets[c + 1]) return fail(2, "cell_offsets not monotonic");
+    for (int k = 0; k < num_cyl_indices; ++k)
+        if (cyl_indices[k] < 0 || cyl_indices[k] >= num_cylinders) return fail(2, "cyl_indices entry out of range");
+    return assemble_common(cylinders, num_cylinders, res, density_multiplier, grid_dim, cell_offsets, cyl_indices,
+                           num_cyl_indices, out_volume);
+}
+
+}  // extern "C"

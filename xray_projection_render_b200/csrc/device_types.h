@@ -1,0 +1,61 @@
+// device_types.h -- kernel parameter blocks shared by api.cu and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace xr {
+
+struct VoxelDev {
+    const void* data;  // device, layout idx = z*NX*NY + x*NY + y
+    int nx, ny, nz;
+    int dtype;  // 0 f32, 1 f64
+};
+
+struct SceneDev {
+    const Instr* instr;
+    const float4* f32;
+    const double* f64;
+    const unsigned long long* grids;
+    const DeformRec* deform;
+    int n_instr, n_deform, f32_count, save_depth;
+    const VoxelDev* vox;  // device table of kMaxVoxelSlots entries
+};
+
+// Per-view camera, fp64, prepared on the host.
+struct CamDev {
+    double eye[3];
+    double view[16];  // row-major camera->world
+    double f;         // 1/tan(fov/2), main.go:457
+};
+
+struct RenderParams {
+    SceneDev scene;
+    const CamDev* cams;
+    int n_views, res;
+    int tiles_i, tiles_j;
+    // Sample lattice (ray independent, built on the host by fp64 repeated addition):
+    //   simple:       s_tab[k] = k-th value of `for s := smin; s < smax; s += ds`, k in [0, n_steps)
+    //   hierarchical: s_tab[0] = smin, s_tab[k+1] = k-th `right`, k in [0, n_steps)
+    // t_tab[k] = float(s_tab[k] - s_center).
+    const double* s_tab;
+    const float* t_tab;
+    int n_steps;
+    double ds;         // step (coarse DS for hierarchical)
+    double ds_fine;    // DS / 10.0
+    double smin, smax, s_center;
+    double flat_field, dm;
+    double aabb_lo[3], aabb_hi[3];
+    void* out;
+    int out_f64;
+    int prog_in_smem;           // stage instr + fp32 pool in shared memory
+    unsigned int smem_prog_bytes;
+    unsigned long long* stats;  // device, XRAY_NUM_STATS counters or null
+};
+
+constexpr int kBlockThreads = 128;
+constexpr int kTileI = 8, kTileJ = 16;  // CTA tile in pixels; warp tile 4 (i) x 8 (j)
+constexpr int kQueueCap = 8;            // deferred refinements per lane before a flush
+
+}  // namespace xr
