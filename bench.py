@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-pixel projection hot path.
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch: all views of the workload (per rank).
+Default workload = BASELINE.json configs[1]: tests/scenes/lattice.json (= examples/lattice.yaml),
+360 views at 1024x1024, hierarchical integrator, auto ds, R=4, fov=40, polar=90, fp32 mode.
+N>1 (torchrun, one rank per GPU): weak scaling -- the global view list has N*views equispaced
+azimuths, rank r renders views r, r+N, ... (the reference's --jobs_modulo/--job sharding); no
+data-path collective.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+SCENES = ROOT / "tests" / "scenes"
+
+# workload name -> (object file, deformation file, views, res, integrator, ds (<=0 auto))
+WORKLOADS = {
+    "cube_w_hole": ("cube_w_hole.json", None, 1, 512, "hierarchical", -1.0),                  # configs[0]
+    "lattice": ("lattice.json", None, 360, 1024, "hierarchical", -1.0),                        # configs[1]
+    "gyroid_sigmoid": ("gyroid_example.json", "deformation_sigmoid.json", 720, 1024, "hierarchical", -1.0),  # configs[2]
+    "voxel1024": (None, None, 1440, 2048, "simple", -1.0),                                     # configs[3] (8 GPUs)
+    "pillar_array": ("pillar_array.json", None, 2880, 4096, "hierarchical", -1.0),             # configs[4]
+}
+R_CAM, FOV, POLAR = 4.0, 40.0, 90.0
+
+# Algorithmic fp32 flops (FMA = 2), SURVEY.md 8(d): per evaluated sample and per primitive test.
+FLOPS_POSITION = 6
+FLOPS_TESS = 27          # 12 bound compares + fold 15
+FLOPS_PRIM = {"cylinder": 25 + 2, "sphere": 9, "box": 9, "cube": 9, "parallelepiped": 24, "gyroid": 13 + 72}
+FLOPS_COLLECTION = 2     # clamp; +1 per child test is folded into the primitive figure below
+
+
+def scene_flops_model(obj: dict, deform: dict | None):
+    """(flops per evaluated sample, flops per primitive test) for roofline accounting."""
+    per_sample = FLOPS_POSITION
+    if deform:
+        per_sample += {"sigmoid": 6 + 12 + 2, "linear": 18, "affine": 15, "rigid": 3, "gaussian": 3 * 14 + 8}.get(deform["type"], 0)
+    prim = []
+
+    def walk(o):
+        nonlocal per_sample
+        t = o["type"]
+        if t == "tessellated_obj_coll":
+            per_sample += FLOPS_TESS + FLOPS_COLLECTION
+            for c in o["uc"]["objects"]["objects"]:
+                walk(c)
+        elif t == "object_collection":
+            per_sample += FLOPS_COLLECTION
+            for c in o["objects"]:
+                walk(c)
+        elif t == "voxel_grid":
+            prim.append(3 + 6 + 14)
+        else:
+            prim.append(FLOPS_PRIM[t] + 1)
+
+    walk(obj)
+    return per_sample, (sum(prim) / len(prim) if prim else 0.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_volume(n: int) -> np.ndarray:
+    """clamp(0.5+0.5 sin(6 pi x) sin(10 pi y) sin(14 pi z), 0, 1) * [r < 0.9], layout [z][x][y]."""
+    ax = (2.0 * np.arange(n, dtype=np.float64) / (n - 1) - 1.0)
+    sx, sy, sz = np.sin(6 * np.pi * ax), np.sin(10 * np.pi * ax), np.sin(14 * np.pi * ax)
+    vol = np.empty((n, n, n), dtype=np.float32)
+    r2x = ax * ax
+    for k in range(n):
+        v = 0.5 + 0.5 * sz[k] * np.outer(sx, sy)
+        mask = (r2x[:, None] + r2x[None, :] + r2x[k]) < 0.81
+        vol[k] = (np.clip(v, 0.0, 1.0) * mask).astype(np.float32)
+    return vol
+
+
+def rank_views(total_views: int, rank: int, world: int):
+    from xray_projection_render_b200 import generate_camera_angles
+
+    return generate_camera_angles(total_views, rank, world, False, POLAR)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline (oracle = C++ restatement of the Go path; kind "port")
+# ----------------------------------------------------------------------------------------
+def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
+    from oracle import oracle as O
+
+    obj, deform, views, res, integ, ds = WORKLOADS[workload]
+    if obj is None:
+        n = 256
+        vol = synthetic_volume(n)
+        osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)})
+        ds_v = 2.0 / 1024 / 5.0  # the full-size workload's step: same per-sample cost model
+        sample_res = 64
+    else:
+        osc = O.OracleScene(str(SCENES / obj), str(SCENES / deform) if deform else None)
+        ds_v = osc.auto_ds() if ds <= 0 else ds
+        sample_res = min(res, 256)
+    threads = nthreads or O.max_threads()
+    angles = O.generate_camera_angles(views)
+    # calibrate on a thin strip, then size the sample for ~budget_s of CPU work
+    eye, cm = O.camera_from_angles(*angles[0], R_CAM)
+    mid = sample_res // 2
+    t0 = time.perf_counter()
+    _, n0 = osc.render_view(eye, cm, sample_res, FOV, R_CAM, ds_v, integ, rows=(mid, mid + max(1, threads // 4)), nthreads=threads)
+    dt0 = max(time.perf_counter() - t0, 1e-4)
+    rows_per_s = max(1, threads // 4) / dt0
+    want_rows = int(min(64 * sample_res, max(threads, rows_per_s * budget_s)))
+    n_views = max(1, min(64, -(-want_rows // sample_res)))
+    rows_each = max(1, min(sample_res, want_rows // n_views))
+    r0 = (sample_res - rows_each) // 2
+    picks = [angles[(len(angles) * k) // n_views] for k in range(n_views)]
+    samples = rays = 0
+    t0 = time.perf_counter()
+    for az, pol in picks:
+        eye, cm = O.camera_from_angles(az, pol, R_CAM)
+        _, n = osc.render_view(eye, cm, sample_res, FOV, R_CAM, ds_v, integ, rows=(r0, r0 + rows_each), nthreads=threads)
+        samples += n
+        rays += rows_each * sample_res
+    dt = time.perf_counter() - t0
+    desc = (f"{n_views} views x {rows_each} central rows at {sample_res}^2 of {workload} ({rays} rays, {samples} samples, "
+            f"{dt:.1f} s); per-ray cost is resolution independent")
+    return {"gsamples_per_s": samples / dt / 1e9, "rays_per_s": rays / dt, "cores": threads, "kind": "port",
+            "sample": desc, "seconds": dt}
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU implementation of the path (C++ restatement of the Go
+    code, all host threads) on the same workload/metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    vals = []
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(args.workload, budget_s=2.0)
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        vals.append(cpu_baseline(args.workload, budget_s=args.cpu_budget / steps))
+    wall = time.perf_counter() - t_all
+    v = float(np.mean([x["gsamples_per_s"] for x in vals]))
+    rays = float(np.mean([x["rays_per_s"] for x in vals]))
+    obj, deform, views, res, integ, ds = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "Gsamples/s", "value": v, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "projections_512_per_s": rays / 262144.0,
+        "config": {"workload": f"{args.workload}: {obj or 'synthetic 1024^3 volume'}, {views} views at {res}x{res}, {integ}, "
+                               f"R={R_CAM}, fov={FOV}, polar={POLAR}", "note": "CPU path timed on a bounded sample (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": v, "unit": "Gsamples/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+        "e2e": {"value": v, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# Our arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    import xray_projection_render_b200 as X
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    obj, deform, views, res, integ, ds = WORKLOADS[args.workload]
+    if args.views:
+        views = args.views
+    if args.res:
+        res = args.res
+    angles = rank_views(views * world, rank, world)
+    cams = X.cameras_from_angles(angles, R_CAM, FOV)
+    n = len(cams)
+    stream = torch.cuda.current_stream()
+    out_dev = torch.empty((n, res, res), dtype=torch.float32, device=dev)
+    out_host = torch.empty((n, res, res), dtype=torch.float32, pin_memory=True)
+    stats = (ctypes.c_uint64 * X._lib.XRAY_NUM_STATS)()
+
+    is_volume = obj is None
+    if is_volume:
+        nvox = args.volume_n
+        vol_host = torch.from_numpy(synthetic_volume(nvox)).pin_memory() if rank == 0 else None
+        vol_dev = torch.empty((nvox, nvox, nvox), dtype=torch.float32, device=dev)
+        if rank == 0:
+            vol_dev.copy_(vol_host, non_blocking=True)
+        if dist is not None:
+            dist.broadcast(vol_dev, src=0)  # the only collective: replicate the volume over NVLink
+        ds_v = 2.0 / nvox / 5.0
+        h2d = vol_dev.numel() * 4 if rank == 0 else 0
+
+        def step_device(st=None):
+            X.render_volume_device(vol_dev, (nvox, nvox, nvox), cams, res, out_dev, ds=ds_v, stream=stream.cuda_stream, stats=st)
+
+        vol_np = vol_host.numpy() if rank == 0 else synthetic_volume(nvox)
+
+        def step_e2e():
+            X.render_volume(vol_np, cams, res, ds=ds_v, out=out_host.numpy())
+
+        per_sample, per_prim = 3 + 6, 14 + 2
+        scene = None
+        h2d_step = vol_dev.numel() * 4
+    else:
+        scene = X.Scene(str(SCENES / obj), str(SCENES / deform) if deform else None)
+        ds_v = scene.auto_ds() if ds <= 0 else ds
+        per_sample, per_prim = scene_flops_model(scene.object_map, scene.deformation_map)
+
+        def step_device(st=None):
+            X.render_scene_device(scene, cams, res, out_dev, integration=integ, precision="fp32", ds=ds_v,
+                                  stream=stream.cuda_stream, stats=st)
+
+        def step_e2e():
+            X.render_scene(scene, cams, res, integration=integ, precision="fp32", ds=ds_v, out=out_host.numpy())
+
+        h2d_step = len(scene.program_bytes()) + n * ctypes.sizeof(X._lib.XRayCameraParams64) + 12 * int(3.48 / ds_v + 2)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peak_tflops = X.measure_fp32_peak()
+
+    # ---- kernel-resident arm: inputs (program / volume) already in HBM, output stays in HBM ----
+    # work counters come from ONE untimed pass of the counting kernel variant; the timed passes
+    # run the production variant (no counters)
+    step_device(stats)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict the previous step's lines from L2 (not timed)
+        evs[k][0].record(stream)
+        step_device()
+        evs[k][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    st = {k: int(stats[i]) * args.steps for i, k in enumerate(("ref_samples", "evaluated_samples", "fp64_fallbacks", "primitive_tests", "rays", "launches"))}
+
+    # ---- end-to-end arm: public host API, host buffers, H2D + D2H inside the timed region ----
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks: max time, sum of work ----
+    vec = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    work = torch.tensor([st["ref_samples"], st["rays"], st["evaluated_samples"], st["primitive_tests"], st["launches"],
+                         st["fp64_fallbacks"]], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = (float(x) for x in vec.tolist())
+    ref_samples, rays, evaluated, prim_tests, launches, fallbacks = (float(x) for x in work.tolist())
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    secs = dev_ms_max / 1e3
+    gsamples = ref_samples / secs / 1e9
+    rays_s = rays / secs
+    e2e_secs = e2e_ms_max / 1e3
+    e2e_gs = ref_samples / e2e_secs / 1e9
+    # roofline of the dominant (only) kernel in the timed region
+    alg_flops = evaluated * per_sample + prim_tests * per_prim  # all ranks, all steps
+    kernel_ms = dev_ms_max / max(1.0, launches / world) if launches else dev_ms_max
+    achieved = alg_flops / world / secs / 1e12  # per GPU TFLOP/s
+    roof = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
+            "traffic": None, "peak_source": "measured in this run: FFMA-chain microbenchmark (XRayMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
+            "algorithmic_flops_per_launch": alg_flops / max(1.0, launches), "avg_launch_ms": kernel_ms,
+            "flops_model": {"per_evaluated_sample": per_sample, "per_primitive_test": per_prim},
+            "evaluated_samples": evaluated, "primitive_tests": prim_tests, "fp64_fallbacks": fallbacks}
+    if is_volume:
+        tap_bytes = evaluated * 32.0
+        roof.update({"bound": "l1", "achieved": tap_bytes / world / secs / 1e9, "unit": "GB/s",
+                     "peak": 128.0 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None})
+        roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
+        roof["peak_source"] = "L1/shared 128 B/clk/SM x 148 SM x measured SM clock (tap stream is served on chip, HBM is <5% utilised)"
+    line = {
+        "metric": "Gsamples/s", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "projections_512_per_s": rays_s / 262144.0, "rays_per_s": rays_s,
+        "config": {"workload": f"{args.workload}: {obj or f'synthetic {args.volume_n}^3 fp32 volume'}, {views} views/GPU at {res}x{res}, "
+                               f"{integ}, ds={ds_v:.6g}, R={R_CAM}, fov={FOV}, polar={POLAR}, fp32 guard-banded mode",
+                   "views_total": views * world, "sharding": "views modulo rank (independent, no data-path collective)",
+                   "l2": "256 MiB buffer rewritten between timed steps; output (>=1.5 GB) exceeds the 126 MB L2"},
+        "e2e": {"value": e2e_gs, "unit": "Gsamples/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(n * res * res * 4),
+                "ms_per_step": e2e_ms_max / args.steps, "projections_512_per_s": rays / e2e_secs / 262144.0,
+                "api": "XRayRenderVolumeExCUDA" if is_volume else "XRayRenderSceneCUDA", "note": "host buffers; images land in pinned host memory"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "wall_s_timed_region": t_wall,
+    }
+    if world == 1 and not args.no_cpu:
+        cb = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {"value": cb["gsamples_per_s"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": cb["kind"],
+                                "sample": cb["sample"], "projections_512_per_s": cb["rays_per_s"] / 262144.0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lattice", choices=sorted(WORKLOADS))
+    ap.add_argument("--views", type=int, default=0, help="override views per GPU (diagnostics only)")
+    ap.add_argument("--res", type=int, default=0, help="override detector size (diagnostics only)")
+    ap.add_argument("--volume-n", type=int, default=1024)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", str(Path(__file__).resolve())] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,7 +99,8 @@ typedef struct {
     uint64_t* stats;           /* optional host array of XRAY_NUM_STATS counters, accumulated:
                                   [0] reference-equivalent samples (density() calls the Go integrator would make)
                                   [1] samples evaluated on the GPU   [2] fp64 re-evaluations in fp32 mode
-                                  [3] primitive tests executed       [4] rays */
+                                  [3] primitive tests executed       [4] rays
+                                  [5] kernel launches */
     int32_t view_begin;        /* first camera's global view index (for sharding bookkeeping only) */
     int32_t reserved[7];
 } XRayRenderOpts;
@@ -109,6 +110,8 @@ typedef struct XRayScene XRayScene; /* opaque: compiled scene (flattened instruc
 /* Thread-local text of the last error returned by any entry point on this thread. */
 const char* XRayLastError(void);
 int XRayDeviceCount(void);
+/* Free the per-device scratch (streams, staging buffers, lattice tables) the library keeps between calls. */
+void XRayReleaseCaches(void);
 void XRayRenderOptsInit(XRayRenderOpts* opts);
 
 /* Compile a scene.  object_json is the object file content as JSON (the schema of

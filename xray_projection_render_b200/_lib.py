@@ -23,7 +23,7 @@ VOXEL_F32, VOXEL_F64 = 0, 1
 
 LEGACY_SYMBOLS = ("AssembleVoxelGridCUDA", "AssembleVoxelGridSpatialCUDA", "RenderVolumeProjectionsCUDA")
 EXTENDED_SYMBOLS = (
-    "XRayLastError", "XRayDeviceCount", "XRayRenderOptsInit", "XRaySceneCompileJSON", "XRaySceneFree",
+    "XRayLastError", "XRayDeviceCount", "XRayReleaseCaches", "XRayRenderOptsInit", "XRaySceneCompileJSON", "XRaySceneFree",
     "XRaySceneMinFeatureSize", "XRaySceneProgram", "XRaySceneBounds", "XRaySceneNumVoxelSlots", "XRaySceneVoxelDims",
     "XRaySceneSetVoxelData", "XRaySceneDensityHost", "XRayCameraFromAngles", "XRayRenderSceneCUDA",
     "XRayRenderSceneDeviceCUDA", "XRayRenderVolumeExCUDA", "XRayRenderVolumeDeviceCUDA", "XRayVoxelizeSceneCUDA",

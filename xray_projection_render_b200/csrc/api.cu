@@ -29,6 +29,9 @@ namespace xr {
 cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream);
 cudaError_t launch_voxelize_scene(const RenderParams& P, int res, float* d_out, cudaStream_t stream);
 cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream);
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, const unsigned char* d_nfine,
+                               int i_coll, int i_tess, cudaStream_t stream);
+size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
                                       const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
@@ -166,6 +169,51 @@ static void build_lattice(int integrator, double ds, double smin, double smax, s
 
 static double focal_from_fov(double fov_deg) { return 1 / std::tan((fov_deg / 2) * M_PI / 180.0); }  // main.go:457
 
+// Number of fine sub-steps the Go loop takes in coarse interval k (main.go:183-189):
+//   left = s_tab[k] + ds; for left < right { ...; left += ds }
+static void build_nfine(const std::vector<double>& s_tab, double ds_fine, std::vector<unsigned char>& nfine) {
+    nfine.assign(s_tab.size(), 0);
+    for (size_t k = 0; k + 1 < s_tab.size(); ++k) {
+        double left = s_tab[k], right = s_tab[k + 1];
+        int n = 0;
+        left += ds_fine;
+        while (left < right && n < 255) {
+            ++n;
+            left += ds_fine;
+        }
+        nfine[k] = (unsigned char)n;
+    }
+}
+
+// Scene shapes with a dedicated fp32 kernel (render_fast.cu): 1 = a primitive or one collection of
+// primitives, 2 = tessellation of one collection of primitives, 0 = generic interpreter.
+static int detect_shape(const XRayScene* sc, int& i_coll, int& i_tess) {
+    const Header* h = (const Header*)sc->blob.data();
+    const Instr* I = (const Instr*)(sc->blob.data() + h->instr_off);
+    const int n = (int)h->n_instr;
+    auto is_prim = [](uint32_t op) { return op >= OP_SPHERE && op <= OP_GYROID; };
+    auto coll_of_prims = [&](int c) -> bool {
+        if (I[c].op != OP_COLL_BEGIN) return false;
+        const int e = (int)I[c].skip_to;
+        if (e <= c || e >= n || I[e].op != OP_COLL_END) return false;
+        for (int k = c + 1; k < e; ++k)
+            if (!is_prim(I[k].op)) return false;
+        return true;
+    };
+    i_coll = i_tess = 0;
+    if (n >= 2 && is_prim(I[0].op) && I[0].n == 1 && I[1].op == OP_END) return 1;
+    if (coll_of_prims(0) && I[I[0].skip_to + 1].op == OP_END) return 1;
+    if (n >= 5 && I[0].op == OP_TESS_BEGIN && coll_of_prims(1)) {
+        const int e = (int)I[1].skip_to;
+        if (I[e + 1].op == OP_TESS_END && I[e + 2].op == OP_END) {
+            i_tess = 0;
+            i_coll = 1;
+            return 2;
+        }
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // One device's share of a render
 // ---------------------------------------------------------------------------------------
@@ -188,64 +236,95 @@ struct Job {
     std::string err;
 };
 
-static int run_job(Job& J) {
-    cudaError_t e;
-    CU(3, cudaSetDevice(J.dev));
-    cudaStream_t stream = J.user_stream;
-    bool own_stream = false;
-    if (!J.use_user_stream) {
-        CU(3, cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        own_stream = true;
-    }
-    int rc = 0;
-    const int nv = (int)J.views.size();
-    const int res = J.res;
-    const size_t esz = J.opts.out_dtype == XRAY_OUT_F64 ? 8 : 4;
-    const size_t img_bytes = (size_t)res * res * esz;
+// Persistent per-device scratch: grow-only buffers, cached sample-lattice tables, one stream.
+// Keeps the steady-state render path free of cudaMalloc/cudaFree (both synchronise the device).
+struct DevCtx {
+    std::mutex mu;
+    int dev = -1;
+    cudaStream_t stream = nullptr;
     CamDev* d_cams = nullptr;
+    size_t cams_cap = 0;
     double* d_s = nullptr;
     float* d_t = nullptr;
+    unsigned char* d_nfine = nullptr;
+    size_t tab_cap = 0;
+    int tab_integ = -1;
+    double tab_ds = 0, tab_smin = 0, tab_smax = 0;
+    int tab_steps = 0;
     unsigned long long* d_stats = nullptr;
     unsigned char* d_img[2] = {nullptr, nullptr};
+    size_t img_cap = 0;
     unsigned char* h_pin[2] = {nullptr, nullptr};
+    size_t pin_cap = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    std::vector<CamDev> hc(nv);
-    std::vector<double> s_tab;
-    std::vector<float> t_tab;
-    DevScene* ds = nullptr;
-    RenderParams P = {};
+    CamDev* h_cams = nullptr;  // pinned staging for the camera upload
+    size_t h_cams_cap = 0;
+};
+static std::mutex g_ctx_mu;
+static std::map<int, DevCtx*> g_ctx;
 
-    auto cleanup = [&]() {
-        if (d_cams) cudaFree(d_cams);
-        if (d_s) cudaFree(d_s);
-        if (d_t) cudaFree(d_t);
-        if (d_stats) cudaFree(d_stats);
-        for (int b = 0; b < 2; ++b) {
-            if (d_img[b]) cudaFree(d_img[b]);
-            if (h_pin[b]) cudaFreeHost(h_pin[b]);
-            if (ev[b]) cudaEventDestroy(ev[b]);
-        }
-        if (own_stream) cudaStreamDestroy(stream);
-    };
+static DevCtx* ctx_for(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(dev);
+    if (it != g_ctx.end()) return it->second;
+    DevCtx* c = new DevCtx();
+    c->dev = dev;
+    g_ctx[dev] = c;
+    return c;
+}
+
+static void ctx_release(DevCtx* c) {
+    cudaSetDevice(c->dev);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->d_cams) cudaFree(c->d_cams);
+    if (c->d_s) cudaFree(c->d_s);
+    if (c->d_t) cudaFree(c->d_t);
+    if (c->d_nfine) cudaFree(c->d_nfine);
+    if (c->d_stats) cudaFree(c->d_stats);
+    if (c->h_cams) cudaFreeHost(c->h_cams);
+    for (int b = 0; b < 2; ++b) {
+        if (c->d_img[b]) cudaFree(c->d_img[b]);
+        if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
+        if (c->ev[b]) cudaEventDestroy(c->ev[b]);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->stream = nullptr;
+    c->d_cams = nullptr; c->cams_cap = 0;
+    c->d_s = nullptr; c->d_t = nullptr; c->d_nfine = nullptr; c->tab_cap = 0; c->tab_integ = -1;
+    c->d_stats = nullptr;
+    c->h_cams = nullptr; c->h_cams_cap = 0;
+    for (int b = 0; b < 2; ++b) { c->d_img[b] = nullptr; c->h_pin[b] = nullptr; c->ev[b] = nullptr; }
+    c->img_cap = 0; c->pin_cap = 0;
+}
+
+static int run_job(Job& J) {
+    cudaError_t e;
+    int rc = 0;
+    CU(3, cudaSetDevice(J.dev));
+    DevCtx* C = ctx_for(J.dev);
+    std::lock_guard<std::mutex> ctx_lock(C->mu);
 #define CUJ(code, call)                               \
     do {                                              \
         e = (call);                                   \
         if (e != cudaSuccess) {                       \
             rc = fail_cuda(code, #call, e);           \
             J.err = g_last_error;                     \
-            cleanup();                                \
             return rc;                                \
         }                                             \
     } while (0)
+    if (!C->stream) CUJ(3, cudaStreamCreateWithFlags(&C->stream, cudaStreamNonBlocking));
+    cudaStream_t stream = J.use_user_stream ? J.user_stream : C->stream;
+    const int nv = (int)J.views.size();
+    if (nv == 0) return 0;
+    const int res = J.res;
+    const size_t esz = J.opts.out_dtype == XRAY_OUT_F64 ? 8 : 4;
+    const size_t img_bytes = (size_t)res * res * esz;
+    RenderParams P = {};
 
-    if (nv == 0) {
-        cleanup();
-        return 0;
-    }
+    DevScene* ds = nullptr;
     rc = ensure_dev_scene(J.scene, J.dev, stream, J.borrowed_vox, &ds);
     if (rc) {
         J.err = g_last_error;
-        cleanup();
         return rc;
     }
     const Header* h = (const Header*)J.scene->blob.data();
@@ -257,30 +336,71 @@ static int run_job(Job& J) {
     P.s_center = R;
     P.ds = J.ds;
     P.ds_fine = J.ds / 10.0;  // main.go:178
-    build_lattice(J.opts.integration, J.ds, P.smin, P.smax, s_tab);
-    P.n_steps = J.opts.integration == XRAY_INTEGRATE_SIMPLE ? (int)s_tab.size() : (int)s_tab.size() - 1;
-    t_tab.resize(s_tab.size());
-    for (size_t k = 0; k < s_tab.size(); ++k) t_tab[k] = (float)(s_tab[k] - P.s_center);
+    int i_coll = 0, i_tess = 0;
+    int shape = detect_shape(J.scene, i_coll, i_tess);
+    if (getenv("XRAY_GENERIC_KERNEL")) shape = 0;
+
+    // sample lattice: cached on the device while (integrator, ds, window) stay the same
+    if (C->tab_integ != J.opts.integration || C->tab_ds != J.ds || C->tab_smin != P.smin || C->tab_smax != P.smax) {
+        std::vector<double> s_tab;
+        std::vector<float> t_tab;
+        std::vector<unsigned char> nfine;
+        build_lattice(J.opts.integration, J.ds, P.smin, P.smax, s_tab);
+        t_tab.resize(s_tab.size());
+        for (size_t k = 0; k < s_tab.size(); ++k) t_tab[k] = (float)(s_tab[k] - P.s_center);
+        if (J.opts.integration == XRAY_INTEGRATE_HIERARCHICAL) build_nfine(s_tab, P.ds_fine, nfine);
+        else nfine.assign(s_tab.size(), 0);
+        const size_t need = std::max<size_t>(16, s_tab.size());
+        CUJ(7, cudaStreamSynchronize(stream));  // earlier launches may still read the old tables
+        if (need > C->tab_cap) {
+            if (C->d_s) cudaFree(C->d_s);
+            if (C->d_t) cudaFree(C->d_t);
+            if (C->d_nfine) cudaFree(C->d_nfine);
+            C->d_s = nullptr; C->d_t = nullptr; C->d_nfine = nullptr; C->tab_cap = 0;
+            CUJ(3, cudaMalloc(&C->d_s, sizeof(double) * need));
+            CUJ(3, cudaMalloc(&C->d_t, sizeof(float) * need));
+            CUJ(3, cudaMalloc(&C->d_nfine, need));
+            C->tab_cap = need;
+        }
+        if (!s_tab.empty()) {
+            CUJ(4, cudaMemcpy(C->d_s, s_tab.data(), sizeof(double) * s_tab.size(), cudaMemcpyHostToDevice));
+            CUJ(4, cudaMemcpy(C->d_t, t_tab.data(), sizeof(float) * t_tab.size(), cudaMemcpyHostToDevice));
+            CUJ(4, cudaMemcpy(C->d_nfine, nfine.data(), nfine.size(), cudaMemcpyHostToDevice));
+        }
+        C->tab_integ = J.opts.integration;
+        C->tab_ds = J.ds;
+        C->tab_smin = P.smin;
+        C->tab_smax = P.smax;
+        C->tab_steps = J.opts.integration == XRAY_INTEGRATE_SIMPLE ? (int)s_tab.size() : (int)s_tab.size() - 1;
+    }
+    P.n_steps = C->tab_steps;
+    P.s_tab = C->d_s;
+    P.t_tab = C->d_t;
+
+    // cameras: pinned staging -> device, ordered on the stream
+    if ((size_t)nv > C->cams_cap) {
+        CUJ(7, cudaStreamSynchronize(stream));
+        if (C->d_cams) cudaFree(C->d_cams);
+        if (C->h_cams) cudaFreeHost(C->h_cams);
+        C->d_cams = nullptr; C->h_cams = nullptr; C->cams_cap = 0;
+        const size_t cap = std::max<size_t>(64, (size_t)nv * 2);
+        CUJ(3, cudaMalloc(&C->d_cams, sizeof(CamDev) * cap));
+        CUJ(3, cudaMallocHost(&C->h_cams, sizeof(CamDev) * cap));
+        C->cams_cap = cap;
+    } else {
+        CUJ(7, cudaStreamSynchronize(stream));  // the staging buffer may still be in flight from the previous call
+    }
     for (int v = 0; v < nv; ++v) {
         const XRayCameraParams64& c = J.cams[J.views[v]];
-        memcpy(hc[v].eye, c.eye, sizeof(c.eye));
-        memcpy(hc[v].view, c.view, sizeof(c.view));
-        hc[v].f = focal_from_fov(c.fov_y);
+        memcpy(C->h_cams[v].eye, c.eye, sizeof(c.eye));
+        memcpy(C->h_cams[v].view, c.view, sizeof(c.view));
+        C->h_cams[v].f = focal_from_fov(c.fov_y);
     }
-    CUJ(3, cudaMalloc(&d_cams, sizeof(CamDev) * nv));
-    CUJ(4, cudaMemcpyAsync(d_cams, hc.data(), sizeof(CamDev) * nv, cudaMemcpyHostToDevice, stream));
-    CUJ(3, cudaMalloc(&d_s, sizeof(double) * std::max<size_t>(1, s_tab.size())));
-    CUJ(3, cudaMalloc(&d_t, sizeof(float) * std::max<size_t>(1, t_tab.size())));
-    if (!s_tab.empty()) {
-        CUJ(4, cudaMemcpyAsync(d_s, s_tab.data(), sizeof(double) * s_tab.size(), cudaMemcpyHostToDevice, stream));
-        CUJ(4, cudaMemcpyAsync(d_t, t_tab.data(), sizeof(float) * t_tab.size(), cudaMemcpyHostToDevice, stream));
-    }
+    CUJ(4, cudaMemcpyAsync(C->d_cams, C->h_cams, sizeof(CamDev) * nv, cudaMemcpyHostToDevice, stream));
     if (J.opts.stats) {
-        CUJ(3, cudaMalloc(&d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS));
-        CUJ(4, cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * XRAY_NUM_STATS, stream));
+        if (!C->d_stats) CUJ(3, cudaMalloc(&C->d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS));
+        CUJ(4, cudaMemsetAsync(C->d_stats, 0, sizeof(unsigned long long) * XRAY_NUM_STATS, stream));
     }
-    P.s_tab = d_s;
-    P.t_tab = d_t;
     P.res = res;
     P.tiles_i = (res + kTileI - 1) / kTileI;
     P.tiles_j = (res + kTileJ - 1) / kTileJ;
@@ -291,7 +411,7 @@ static int run_job(Job& J) {
         P.aabb_hi[a] = h->aabb_hi[a];
     }
     P.out_f64 = J.opts.out_dtype == XRAY_OUT_F64;
-    P.stats = d_stats;
+    P.stats = J.opts.stats ? C->d_stats : nullptr;
     {
         size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
         size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));
@@ -300,13 +420,12 @@ static int run_job(Job& J) {
         P.smem_prog_bytes = P.prog_in_smem ? (unsigned int)prog : 0u;
     }
 
-    // Contiguity: views of this job that are adjacent in the output can share one launch.
-    // Batch = run of views; device-resident output renders straight into place when the views
-    // are consecutive, otherwise view by view.
     const size_t max_batch_bytes = (size_t)256 << 20;
     int max_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nv, max_batch_bytes / img_bytes));
+    unsigned long long n_launches = 0;
     auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
-        P.cams = d_cams + v0;
+        ++n_launches;
+        P.cams = C->d_cams + v0;
         P.n_views = n;
         P.out = d_dst;
         // the grid is one CTA per (view, tile); keep it below 2^31
@@ -314,10 +433,13 @@ static int run_job(Job& J) {
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
+        if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && P.prog_in_smem && fast_kernel_smem_bytes(P) <= 200 * 1024)
+            return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, C->d_nfine, i_coll, i_tess, stream);
         return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
     };
 
     if (J.out_on_device) {
+        // views of this job that are adjacent in the output share one launch
         int v = 0;
         while (v < nv) {
             int n = 1;
@@ -329,19 +451,37 @@ static int run_job(Job& J) {
         cudaPointerAttributes attr;
         bool out_pinned = cudaPointerGetAttributes(&attr, J.out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         cudaGetLastError();
-        for (int b = 0; b < 2; ++b) {
-            CUJ(3, cudaMalloc(&d_img[b], (size_t)max_batch * img_bytes));
-            if (!out_pinned) CUJ(3, cudaMallocHost(&h_pin[b], (size_t)max_batch * img_bytes));
-            CUJ(3, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+        const size_t need = (size_t)max_batch * img_bytes;
+        if (need > C->img_cap) {
+            CUJ(7, cudaStreamSynchronize(stream));
+            for (int b = 0; b < 2; ++b) {
+                if (C->d_img[b]) cudaFree(C->d_img[b]);
+                C->d_img[b] = nullptr;
+            }
+            C->img_cap = 0;
+            for (int b = 0; b < 2; ++b) CUJ(3, cudaMalloc(&C->d_img[b], need));
+            C->img_cap = need;
         }
+        if (!out_pinned && need > C->pin_cap) {
+            CUJ(7, cudaStreamSynchronize(stream));
+            for (int b = 0; b < 2; ++b) {
+                if (C->h_pin[b]) cudaFreeHost(C->h_pin[b]);
+                C->h_pin[b] = nullptr;
+            }
+            C->pin_cap = 0;
+            for (int b = 0; b < 2; ++b) CUJ(3, cudaMallocHost(&C->h_pin[b], need));
+            C->pin_cap = need;
+        }
+        for (int b = 0; b < 2; ++b)
+            if (!C->ev[b]) CUJ(3, cudaEventCreateWithFlags(&C->ev[b], cudaEventDisableTiming));
         int pend_v0[2] = {0, 0}, pend_n[2] = {0, 0};
         auto drain = [&](int b) -> cudaError_t {  // copy batch b from pinned staging into the caller's buffer
             if (pend_n[b] == 0) return cudaSuccess;
-            cudaError_t ee = cudaEventSynchronize(ev[b]);
+            cudaError_t ee = cudaEventSynchronize(C->ev[b]);
             if (ee != cudaSuccess) return ee;
             if (!out_pinned)
                 for (int k = 0; k < pend_n[b]; ++k)
-                    memcpy((unsigned char*)J.out + (size_t)J.views[pend_v0[b] + k] * img_bytes, h_pin[b] + (size_t)k * img_bytes,
+                    memcpy((unsigned char*)J.out + (size_t)J.views[pend_v0[b] + k] * img_bytes, C->h_pin[b] + (size_t)k * img_bytes,
                            img_bytes);
             pend_n[b] = 0;
             return cudaSuccess;
@@ -350,15 +490,21 @@ static int run_job(Job& J) {
         while (v < nv) {
             int n = std::min(max_batch, nv - v);
             CUJ(7, drain(b));  // buffer b is free again once its previous batch reached the caller
-            CUJ(5, launch(v, n, d_img[b]));
+            CUJ(5, launch(v, n, C->d_img[b]));
             if (out_pinned) {
-                for (int k = 0; k < n; ++k)
+                // contiguous runs of views go out in one copy each
+                int k = 0;
+                while (k < n) {
+                    int m = 1;
+                    while (k + m < n && J.views[v + k + m] == J.views[v + k + m - 1] + 1) ++m;
                     CUJ(8, cudaMemcpyAsync((unsigned char*)J.out + (size_t)J.views[v + k] * img_bytes,
-                                           d_img[b] + (size_t)k * img_bytes, img_bytes, cudaMemcpyDeviceToHost, stream));
+                                           C->d_img[b] + (size_t)k * img_bytes, (size_t)m * img_bytes, cudaMemcpyDeviceToHost, stream));
+                    k += m;
+                }
             } else {
-                CUJ(8, cudaMemcpyAsync(h_pin[b], d_img[b], (size_t)n * img_bytes, cudaMemcpyDeviceToHost, stream));
+                CUJ(8, cudaMemcpyAsync(C->h_pin[b], C->d_img[b], (size_t)n * img_bytes, cudaMemcpyDeviceToHost, stream));
             }
-            CUJ(7, cudaEventRecord(ev[b], stream));
+            CUJ(7, cudaEventRecord(C->ev[b], stream));
             pend_v0[b] = v;
             pend_n[b] = n;
             v += n;
@@ -368,19 +514,12 @@ static int run_job(Job& J) {
         CUJ(7, drain(b ^ 1));
     }
     if (J.opts.stats) {
-        CUJ(8, cudaMemcpyAsync(J.stats, d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS, cudaMemcpyDeviceToHost, stream));
+        CUJ(8, cudaMemcpyAsync(J.stats, C->d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS, cudaMemcpyDeviceToHost, stream));
         CUJ(7, cudaStreamSynchronize(stream));
+        J.stats[5] = n_launches;
     } else if (!J.out_on_device) {
         CUJ(7, cudaStreamSynchronize(stream));
     }
-    if (J.out_on_device && !J.use_user_stream) CUJ(7, cudaStreamSynchronize(stream));
-    if (J.out_on_device && J.use_user_stream) {
-        // scratch (cams, tables) is freed below: cudaFree synchronises with outstanding work on
-        // the device, so the asynchronous contract holds for the caller-visible buffers only
-        // after this point; keep the cost off the hot path by retiring scratch via the stream.
-        CUJ(7, cudaStreamSynchronize(stream));
-    }
-    cleanup();
     return 0;
 #undef CUJ
 }
@@ -483,6 +622,17 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
 extern "C" {
 
 const char* XRayLastError(void) { return g_last_error.c_str(); }
+
+void XRayReleaseCaches(void) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_ctx) {
+        std::lock_guard<std::mutex> l2(kv.second->mu);
+        ctx_release(kv.second);
+    }
+    cudaSetDevice(cur);
+}
 
 int XRayDeviceCount(void) {
     int n = 0;

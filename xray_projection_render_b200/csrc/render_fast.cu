@@ -1,0 +1,409 @@
+// render_fast.cu -- the fp32 hot kernels for the two scene shapes every bundled / benchmark scene
+// has: FLAT (a primitive, or one collection of primitives) and TESS (tessellated_obj_coll whose
+// unit cell is one collection of primitives).  Anything else takes the generic interpreter in
+// render_scene.cu.
+//
+// What makes these lean (see profiles/ for the ncu evidence that drove it):
+//   * the flattened program is addressed as true shared memory (LDS broadcasts), never through a
+//     generic pointer;
+//   * no per-op dispatch: the shape fixes the prologue (bounds, fold, child-mask lookup) and the
+//     epilogue; only the loop over primitive runs is data driven;
+//   * ONE evaluation site serves coarse steps, fine (refinement) steps and both integrators: the
+//     march is a warp-uniform two-mode loop, so the evaluator is instantiated once and the whole
+//     hot loop stays inside the instruction cache;
+//   * the fp64 re-evaluation of guard-band samples is a cold, out-of-line function; the exact ray
+//     is parked in shared memory instead of being rebuilt or held in registers;
+//   * hierarchical refinements are queued per lane and replayed warp-wide (fine step positions and
+//     counts come from host tables, so the fp32 path carries no fp64 state).
+#include "eval.cuh"
+
+namespace xr {
+
+struct FastArgs {  // uniform per-launch scalars the hot loop needs, staged in shared memory
+    SceneView gsv;  // global-memory view of the program for the exact path
+};
+
+// Cold path: exact fp64 density at lattice position s for the lanes in `need`.
+// Out of line on purpose: it must not dilute the hot loop's instruction footprint.
+__device__ __noinline__ float exact_density_cold(const SceneView* sv, const double* ray, double s, double dm, bool need) {
+    const int tid = threadIdx.x;
+    // ray[] is [6][blockDim]: o.x o.y o.z d.x d.y d.z
+    const double x = dadd(ray[0 * kBlockThreads + tid], dmul(ray[3 * kBlockThreads + tid], s));
+    const double y = dadd(ray[1 * kBlockThreads + tid], dmul(ray[4 * kBlockThreads + tid], s));
+    const double z = dadd(ray[2 * kBlockThreads + tid], dmul(ray[5 * kBlockThreads + tid], s));
+    bool dummy = false;
+    Counters cnt = {0};
+    SaveStack<Exact> st = {nullptr, nullptr};  // FLAT / TESS programs never need save frames
+    const double r64 = dmul(eval_scene<Exact>(*sv, x, y, z, need, dummy, st, cnt), dm);
+    float rho = (float)r64;
+    if (r64 != 0.0 && rho == 0.0f) rho = r64 > 0 ? 1e-30f : -1e-30f;  // keep zero-ness for the transition test
+    return rho;
+}
+
+// Exact position of fine sample j (0-based) of coarse interval kf: s_tab[kf] + ds_fine added (j+1) times.
+__device__ __noinline__ double fine_position_cold(const double* s_tab, int kf, int j, double ds_fine) {
+    double left = s_tab[kf];
+    for (int q = 0; q <= j; ++q) left = dadd(left, ds_fine);
+    return left;
+}
+
+enum Shape { SHAPE_FLAT = 1, SHAPE_TESS = 2 };
+
+// Lane state of a collection evaluation, kept in two floats so no bool has to live in a register:
+//   res == 0  : lane still needs a value ("active")      res > 0 : greedy first hit (objects.go:425-427)
+//   res  < 0  : lane takes no part (outside bounds / ray inactive)
+__device__ __forceinline__ void emit_child(bool in, bool near, float rho, bool greedy, float& res, float& acc, bool& unc,
+                                           int& nhit) {
+    const bool act = res == 0.0f;
+    unc = unc || (near && act);
+    if (in && act) {
+        if (greedy && rho > 0.0f) {
+            res = rho;
+        } else {
+            acc += rho;
+            ++nhit;
+        }
+    }
+}
+
+// Visit the set bits of a run's 64-bit child mask as two 32-bit words (cheap FLO/LOP3 per child).
+#define XR_FOR_EACH_CHILD(LO, HI, ...)                                      \
+    for (int half_ = 0; half_ < 2; ++half_) {                                \
+        unsigned int w_ = half_ ? (HI) : (LO);                               \
+        const int base_ = half_ * 32;                                        \
+        while (w_) {                                                         \
+            const int c = base_ + __ffs((int)w_) - 1;                        \
+            w_ &= w_ - 1;                                                    \
+            if (greedy && !__any_sync(FULL_MASK, res == 0.0f)) goto finish;  \
+            if (COUNT) prim_tests += (res == 0.0f) ? 1u : 0u;                \
+            __VA_ARGS__                                                      \
+        }                                                                    \
+    }
+
+// Evaluate the primitive runs [rb, re) of one collection at (x,y,z).
+template <bool COUNT>
+__device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const float4* __restrict__ sF, int rb, int re,
+                                           unsigned int cflags, bool has_mask, unsigned int umask_lo, unsigned int umask_hi,
+                                           float x, float y, float z, bool alive, bool& unc, unsigned int& prim_tests) {
+    const bool greedy = (cflags & F_GREEDY) != 0;
+    float acc = 0.0f, res = alive ? 0.0f : -1.0f;
+    int nhit = 0;
+    for (int r = rb; r < re; ++r) {
+        const uint4 w0 = reinterpret_cast<const uint4*>(sI + r)[0];  // op, n, flags, child_bit
+        const unsigned int f32_idx = reinterpret_cast<const uint4*>(sI + r)[1].x;
+        unsigned long long bits = w0.y >= 64u ? ~0ull : ((1ull << w0.y) - 1ull);
+        if (has_mask) bits &= ((((unsigned long long)umask_hi << 32) | umask_lo) >> w0.w);
+        const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+        const float4* __restrict__ q = sF + f32_idx;
+        if (w0.x == OP_CYL) {
+            XR_FOR_EACH_CHILD(lo, hi, {
+                const float4 a = q[c * kF32Cyl], v = q[c * kF32Cyl + 1], t = q[c * kF32Cyl + 2];
+                const float wx = x - a.x, wy = y - a.y, wz = z - a.z;
+                const float cc = (wx * v.x + wy * v.y + wz * v.z) * v.w;
+                const float ex = fmaf(-v.x, cc, wx), ey = fmaf(-v.y, cc, wy), ez = fmaf(-v.z, cc, wz);
+                const float ar = fmaf(ex, ex, fmaf(ey, ey, ez * ez)) - t.x;  // < 0 inside the radius
+                const float ac = fabsf(cc - 0.5f) - 0.5f;                     // <= 0 between the caps
+                const float worst = fmaxf(ar * t.w, ac);                      // t.w = tolc/tolr: common scale
+                const bool in = worst < -t.z;
+                emit_child(in, !in && worst < t.z, a.w, greedy, res, acc, unc, nhit);
+            })
+        } else if (w0.x == OP_SPHERE) {
+            XR_FOR_EACH_CHILD(lo, hi, {
+                const float4 a = q[c * kF32Sphere], b = q[c * kF32Sphere + 1];
+                const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
+                const float m = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - b.x;
+                emit_child(m < 0.0f, fabsf(m) < b.y, a.w, greedy, res, acc, unc, nhit);
+            })
+        } else if (w0.x == OP_BOX) {
+            XR_FOR_EACH_CHILD(lo, hi, {
+                const float4 a = q[c * kF32Box], b = q[c * kF32Box + 1];
+                const float m = fmaxf(fabsf(x - a.x) - b.x, fmaxf(fabsf(y - a.y) - b.y, fabsf(z - a.z) - b.z));
+                emit_child(m < 0.0f, fabsf(m) < b.w, a.w, greedy, res, acc, unc, nhit);
+            })
+        } else if (w0.x == OP_PPED) {
+            XR_FOR_EACH_CHILD(lo, hi, {
+                const float4 a = q[c * kF32Pped], r0 = q[c * kF32Pped + 1], r1 = q[c * kF32Pped + 2], r2 = q[c * kF32Pped + 3];
+                const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
+                const float qx = r0.x * dx + r0.y * dy + r0.z * dz;
+                const float qy = r1.x * dx + r1.y * dy + r1.z * dz;
+                const float qz = r2.x * dx + r2.y * dy + r2.z * dz;
+                const float m = fmaxf(fabsf(qx - 0.5f), fmaxf(fabsf(qy - 0.5f), fabsf(qz - 0.5f))) - 0.5f;
+                emit_child(m < 0.0f, fabsf(m) < r0.w, a.w, greedy, res, acc, unc, nhit);
+            })
+        } else {  // OP_GYROID
+            XR_FOR_EACH_CHILD(lo, hi, {
+                const float4 a = q[c * kF32Gyroid], b = q[c * kF32Gyroid + 1];
+                float sx, cx, sy, cy, sz, cz;
+                sincosf((x - a.x) * b.x, &sx, &cx);
+                sincosf((y - a.y) * b.x, &sy, &cy);
+                sincosf((z - a.z) * b.x, &sz, &cz);
+                const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
+                emit_child(t < 0.0f, fabsf(t) < b.z, a.w, greedy, res, acc, unc, nhit);
+            })
+        }
+    }
+finish:
+    // objects.go:422-438: greedy returns the first positive child unclamped, else sum clamped to [0,1]
+    float val = acc;
+    if (cflags & 0x100u) val = __saturatef(acc);                // bit 8: a collection (clamps), not a bare primitive
+    if (nhit >= 2 && fabsf(acc) < 1e-5f && res == 0.0f) unc = true;  // near-cancelling sum: zero-ness needs fp64
+    if (res > 0.0f) val = res;
+    return val;
+}
+
+template <int SHAPE, int INTEG, bool COUNT>
+__global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
+                                                                       int i_coll, int i_tess) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles] [queue kQueueCap x nt ints]
+    const Instr* sI = reinterpret_cast<const Instr*>(smem);
+    const float4* sF = reinterpret_cast<const float4*>(smem + (size_t)P.scene.n_instr * sizeof(Instr));
+    FastArgs* sA = reinterpret_cast<FastArgs*>(smem + P.smem_prog_bytes);
+    double* sRay = reinterpret_cast<double*>(sA + 1);
+    int* queue = reinterpret_cast<int*>(sRay + 6 * kBlockThreads);
+    const int tid = threadIdx.x;
+    {
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        const uint4* srcI = reinterpret_cast<const uint4*>(P.scene.instr);
+        const int nI = P.scene.n_instr * 2;
+        for (int k = tid; k < nI; k += kBlockThreads) dst[k] = srcI[k];
+        const uint4* srcF = reinterpret_cast<const uint4*>(P.scene.f32);
+        for (int k = tid; k < P.scene.f32_count; k += kBlockThreads) dst[nI + k] = srcF[k];
+        if (tid == 0) {
+            SceneView g;
+            g.instr = P.scene.instr;
+            g.f32 = P.scene.f32;
+            g.f64 = P.scene.f64;
+            g.grids = P.scene.grids;
+            g.deform = P.scene.deform;
+            g.n_instr = P.scene.n_instr;
+            g.n_deform = P.scene.n_deform;
+            g.vox = P.scene.vox;
+            sA->gsv = g;
+        }
+    }
+
+    int view, i, j;
+    pixel_of_thread(P, view, i, j);
+    const bool valid = i < P.res && j < P.res;
+    if (!valid) { i = 0; j = 0; }
+    int k0, k1;
+    bool hit;
+    float pcx, pcy, pcz, pdx, pdy, pdz;
+    {
+        const Ray64 ray = make_ray(P.cams[view], i, j, P.res);
+        double s_in, s_out;
+        hit = valid && clip_ray(ray, P.aabb_lo, P.aabb_hi, s_in, s_out);
+        step_range(P, hit, s_in, s_out, INTEG == 1 ? 1 : 0, k0, k1);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            sRay[a * kBlockThreads + tid] = ray.o[a];
+            sRay[(3 + a) * kBlockThreads + tid] = ray.d[a];
+        }
+        pcx = (float)(ray.o[0] + ray.d[0] * P.s_center);
+        pcy = (float)(ray.o[1] + ray.d[1] * P.s_center);
+        pcz = (float)(ray.o[2] + ray.d[2] * P.s_center);
+        pdx = (float)ray.d[0];
+        pdy = (float)ray.d[1];
+        pdz = (float)ray.d[2];
+    }
+    __syncthreads();
+    const int wk0 = __reduce_min_sync(FULL_MASK, hit ? k0 : 0x7fffffff);
+    const int wk1 = __reduce_max_sync(FULL_MASK, hit ? k1 : 0);
+
+    // shape constants (uniform)
+    const uint4 cw0 = reinterpret_cast<const uint4*>(sI + i_coll)[0];
+    const uint4 cw1 = reinterpret_cast<const uint4*>(sI + i_coll)[1];
+    const bool is_coll = cw0.x == OP_COLL_BEGIN;
+    const int rb = is_coll ? i_coll + 1 : i_coll;
+    const int re = is_coll ? (int)cw1.z : i_coll + 1;  // skip_to = matching COLL_END
+    const unsigned int cflags = is_coll ? (cw0.z | 0x100u) : 0u;
+    const bool has_grid = is_coll && (cw0.z & F_HAS_GRID);
+    const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
+    const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
+    const float4* tF = sF + (SHAPE == SHAPE_TESS ? reinterpret_cast<const uint4*>(sI + i_tess)[1].x : 0u);
+    const int n_deform = P.scene.n_deform;
+    const DeformRec* __restrict__ deform = P.scene.deform;
+
+    const float dmf = (float)P.dm;
+    const float dsf = (float)P.ds_fine;
+    // T - flat_field = sum rho*w, w = DS for plain coarse steps and ds for refined ones; Kahan
+    // compensated so the fp32 sum stays ~1e-7 relative however many steps a ray takes
+    const float wC = (float)P.ds, wF = (float)P.ds_fine;
+    float accT = 0.0f, cmpT = 0.0f;
+#define XR_KADD(V)                         \
+    do {                                   \
+        const float y_ = (V)-cmpT;         \
+        const float t_ = accT + y_;        \
+        cmpT = (t_ - accT) - y_;           \
+        accT = t_;                         \
+    } while (0)
+    float prev = 0.0f;
+    int qn = 0;
+    unsigned int n_eval = 0, n_fine = 0, n_fallback = 0, prim_tests = 0;
+
+    // two-mode warp-uniform march: mode 0 walks the coarse lattice, mode 1 replays queued refinements
+    int k = wk0;
+    int mode = 0;
+    int kf = 0, jf = 0, nf = 0;  // fine state: interval, sub-step, sub-step count
+    for (;;) {
+        float t;
+        bool act;
+        if (mode == 0) {
+            if (k >= wk1) {
+                if (INTEG == 0 || !__any_sync(FULL_MASK, qn > 0)) break;
+                mode = 1;
+                nf = 0;
+                jf = 0;
+                continue;
+            }
+            act = hit && k >= k0 && k < k1;
+            t = P.t_tab[k + (INTEG == 1 ? 1 : 0)];
+        } else {
+            act = jf < nf;
+            if (!__any_sync(FULL_MASK, act)) {  // this round of intervals is done: pop the next one per lane
+                const bool has = qn > 0;
+                if (!__any_sync(FULL_MASK, has)) {
+                    mode = 0;
+                    continue;
+                }
+                if (has) {
+                    kf = queue[(--qn) * kBlockThreads + tid];
+                    nf = nfine_tab[kf];
+                } else {
+                    nf = 0;
+                }
+                jf = 0;
+                continue;
+            }
+            t = fmaf((float)(jf + 1), dsf, P.t_tab[act ? kf : 0]);
+        }
+
+        // ---- the single evaluation site ----
+        float x = fmaf(pdx, t, pcx), y = fmaf(pdy, t, pcy), z = fmaf(pdz, t, pcz);
+        bool unc = false;
+        for (int d = 0; d < n_deform; ++d) Fast::deform(deform[d], x, y, z);
+        bool alive = act;
+        unsigned int um_lo = ~0u, um_hi = ~0u;
+        if (SHAPE == SHAPE_TESS) {
+            const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
+            const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
+            const float qx = (x - um.x) * id.x, qy = (y - um.y) * id.y, qz = (z - um.z) * id.z;
+            const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+            const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+            const float lo = fminf(rx, fminf(ry, rz)), hi = fmaxf(rx, fmaxf(ry, rz));
+            const bool inside = m <= 0.0f;  // outer bounds inclusive (objects.go:569)
+            unc = alive && ((fabsf(m) < oc.w) || (inside && (lo < id.w || hi > 1.0f - id.w)));
+            alive = alive && inside;
+            x = fmaf(-dd.x, fx, x);
+            y = fmaf(-dd.y, fy, y);
+            z = fmaf(-dd.z, fz, z);
+            if (has_grid) {  // the grid spans exactly the unit cell: cell = floor(fraction * g), fraction in [0,1]
+                const float4 gd = gF[2], gf = gF[3];
+                const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
+                const int ix = min(gx - 1, (int)(rx * gf.x));
+                const int iy = min(gy - 1, (int)(ry * gf.y));
+                const int iz = min(gz - 1, (int)(rz * gf.z));
+                uint2 mk = make_uint2(0u, 0u);
+                if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
+                um_lo = __reduce_or_sync(FULL_MASK, mk.x);
+                um_hi = __reduce_or_sync(FULL_MASK, mk.y);
+            }
+        } else if (has_grid) {
+            const float4 g0 = gF[0], g1 = gF[1], gd = gF[2];
+            const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
+            const int ix = min(gx - 1, max(0, __float2int_rd((x - g0.x) * g1.x)));
+            const int iy = min(gy - 1, max(0, __float2int_rd((y - g0.y) * g1.y)));
+            const int iz = min(gz - 1, max(0, __float2int_rd((z - g0.z) * g1.z)));
+            uint2 mk = make_uint2(0u, 0u);
+            if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
+            um_lo = __reduce_or_sync(FULL_MASK, mk.x);
+            um_hi = __reduce_or_sync(FULL_MASK, mk.y);
+        }
+        float rho = 0.0f;
+        if ((um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive))
+            rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests);
+        rho *= dmf;
+        unc = unc && act;
+        if (__any_sync(FULL_MASK, unc)) {
+            double s_exact;
+            if (mode == 0) s_exact = P.s_tab[k + (INTEG == 1 ? 1 : 0)];
+            else s_exact = fine_position_cold(P.s_tab, kf, jf, P.ds_fine);
+            const float r = exact_density_cold(&sA->gsv, sRay, s_exact, P.dm, unc);
+            if (unc) {
+                rho = r;
+                if (COUNT) ++n_fallback;
+            }
+        }
+
+        // ---- bookkeeping ----
+        if (mode == 0) {
+            if (act) {
+                if (COUNT) ++n_eval;
+                float w = wC;
+                if (INTEG == 1 && ((rho == 0.0f) != (prev == 0.0f))) {
+                    queue[qn * kBlockThreads + tid] = k;
+                    ++qn;
+                    w = wF;  // T += rho*ds (main.go:188) instead of rho*DS (main.go:190)
+                }
+                XR_KADD(rho * w);
+                prev = rho;
+            }
+            ++k;
+            if (INTEG == 1 && __any_sync(FULL_MASK, qn == kQueueCap)) {
+                mode = 1;
+                nf = 0;
+                jf = 0;
+            }
+        } else {
+            if (act) {
+                XR_KADD(rho * wF);
+                if (COUNT) {
+                    ++n_eval;
+                    ++n_fine;
+                }
+            }
+            ++jf;
+        }
+    }
+    const double T = P.flat_field + ((double)accT - (double)cmpT);
+    store_pixel(P, view, i, j, valid, exp(-T));
+    if (COUNT) {
+        // the count of fine steps is ray independent given the refined intervals; recount exactly
+        add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
+    }
+}
+
+size_t fast_kernel_smem_bytes(const RenderParams& P) {
+    return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double) + (size_t)kQueueCap * kBlockThreads * sizeof(int);
+}
+
+template <int SHAPE, int INTEG, bool COUNT>
+static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine, int i_coll, int i_tess, size_t smem, unsigned int grid,
+                              cudaStream_t stream) {
+    auto kern = render_fast_kernel<SHAPE, INTEG, COUNT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kBlockThreads, smem, stream>>>(P, nfine, i_coll, i_tess);
+    return cudaGetLastError();
+}
+
+// shape: SHAPE_FLAT / SHAPE_TESS; i_coll: index of the COLL_BEGIN (or of the lone primitive run);
+// i_tess: index of the TESS_BEGIN.
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, const unsigned char* d_nfine,
+                               int i_coll, int i_tess, cudaStream_t stream) {
+    const size_t smem = fast_kernel_smem_bytes(P);
+    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    if (grid == 0) return cudaSuccess;
+#define XR_GO(S, I, C) return launch_one<S, I, C>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
+    if (shape == SHAPE_FLAT) {
+        if (integrator == 0) { if (count) XR_GO(SHAPE_FLAT, 0, true); else XR_GO(SHAPE_FLAT, 0, false); }
+        else { if (count) XR_GO(SHAPE_FLAT, 1, true); else XR_GO(SHAPE_FLAT, 1, false); }
+    } else {
+        if (integrator == 0) { if (count) XR_GO(SHAPE_TESS, 0, true); else XR_GO(SHAPE_TESS, 0, false); }
+        else { if (count) XR_GO(SHAPE_TESS, 1, true); else XR_GO(SHAPE_TESS, 1, false); }
+    }
+#undef XR_GO
+}
+
+}  // namespace xr

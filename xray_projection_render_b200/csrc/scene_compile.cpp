@@ -842,7 +842,7 @@ static void emit_prim_params(Builder& B, const Node& n) {
             double tolr = 2.0 * (2.0 * r * (1.7321 * ep + lv * tolc_raw + 6.0 * u * wmax) + 6.0 * u * r * r + 3 * ep * ep);
             B.f4(p[0], p[1], p[2], p[7]);
             B.f4(v[0], v[1], v[2], inv_vv);
-            B.f4(p[6] * p[6], up32(tolr), up32(tolc), 0);
+            B.f4(p[6] * p[6], up32(tolr), up32(tolc), up32(tolc) / up32(tolr));  // .w rescales the radial slack onto tolc
             B.d64(p, 8, kF64Cyl);
             break;
         }
@@ -988,7 +988,7 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
     B.f4(reg.lo[0], reg.lo[1], reg.lo[2], 0);
     B.f4(1.0 / cs[0], 1.0 / cs[1], 1.0 / cs[2], 0);
     B.f4bits((uint32_t)g[0], (uint32_t)g[1], (uint32_t)g[2], 0);
-    B.f4(0, 0, 0, 0);
+    B.f4(g[0], g[1], g[2], 0);  // the same dims as floats (saves three I2F per sample)
     // fp64 copy for the exact path: gmin(3), inv_cell(3)
     return true;
 }
