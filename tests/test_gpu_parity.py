@@ -1,0 +1,202 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- the first gate.
+
+Tolerances are the north star's: fp32 mode per-pixel |dI| <= 1e-4, fp64 mode <= 1e-9 (helpers.py).
+Reference-equivalent sample counts must equal the oracle's density() call counts exactly.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import FOV, R, TOL_FP32, TOL_FP64, assert_parity, gpu_vs_oracle, oracle_images
+
+pytestmark = pytest.mark.gpu
+
+ANALYTIC = ["cube_w_hole", "balls", "box_w_pped", "pillar_array", "lattice"]
+
+
+@pytest.mark.parametrize("integ", ["hierarchical", "simple"])
+@pytest.mark.parametrize("name", ANALYTIC)
+def test_bundled_scenes(X, O, scenes, name, integ):
+    out, nref, _ = gpu_vs_oracle(X, O, str(scenes / f"{name}.json"), integ=integ, res=48)
+    assert_parity(out, nref)
+
+
+def test_gyroid_with_sigmoid_warp(X, O, scenes):  # BASELINE config 3 (coarser step so the oracle finishes in seconds)
+    out, nref, _ = gpu_vs_oracle(X, O, str(scenes / "gyroid_example.json"), str(scenes / "deformation_sigmoid.json"), res=32,
+                                 ds=0.004)
+    assert_parity(out, nref)
+
+
+def test_gyroid_auto_step_single_rows(X, O, scenes):
+    """config 3 at its real step (ds = 4e-4, 8700 coarse steps): a few pixel rows against the oracle."""
+    obj, d = str(scenes / "gyroid_example.json"), str(scenes / "deformation_sigmoid.json")
+    sc, osc = X.Scene(obj, d), O.OracleScene(obj, d)
+    ds = sc.auto_ds()
+    res = 16
+    views = [(100.0, 90.0)]
+    cams = X.cameras_from_angles(views, R, FOV)
+    eye, cm = O.camera_from_angles(*views[0], R)
+    ref, n = osc.render_view(eye, cm, res, FOV, R, ds, "hierarchical", rows=(6, 10))
+    for prec, tol in (("fp32", TOL_FP32), ("fp64", TOL_FP64)):
+        img = X.render_scene(sc, cams, res, precision=prec, ds=ds)
+        assert np.abs(img[0, 6:10].astype(np.float64) - ref[6:10]).max() <= tol
+
+
+DEFORMS = [
+    {"type": "linear", "strains": [0.0, 0.0, 0.0, 0.1, 0.1, 0.1]},
+    {"type": "rigid", "displacements": [0.1, -0.2, 0.05]},
+    {"type": "sigmoid", "amplitude": -0.15, "center": 0.1, "lengthscale": 0.1, "direction": "x"},
+    {"type": "affine", "matrix": [[1.1, 0.2, 0.0], [0.0, 0.9, 0.1], [0.3, 0.0, 1.2]]},
+    {"type": "gaussian", "amplitudes": [0.1, 0.0, -0.1], "sigmas": [0.3, 0.4, 0.5], "centers": [0.1, 0.0, -0.2]},
+    {"type": "composed", "deformations": [{"type": "rigid", "displacements": [0.1, 0.0, 0.0]},
+                                          {"type": "sigmoid", "amplitude": 0.2, "center": 0.0, "lengthscale": 0.2, "direction": "y"},
+                                          {"type": "linear", "strains": [0.01, 0.02, 0.03, 0.0, 0.0, 0.05]}]},
+]
+
+
+@pytest.mark.parametrize("d", DEFORMS, ids=lambda d: d["type"])
+@pytest.mark.parametrize("name", ["cube_w_hole", "pillar_array"])
+def test_deformations(X, O, scenes, name, d):
+    obj = json.loads((scenes / f"{name}.json").read_text())
+    out, nref, _ = gpu_vs_oracle(X, O, obj, d, res=40, ff=0.1, dm=1.7)
+    assert_parity(out, nref)
+
+
+def test_every_primitive_and_negative_densities(X, O):
+    obj = {"type": "object_collection", "objects": [
+        {"type": "box", "center": [0.0, 0.0, 0.0], "sides": [1.4, 1.2, 1.0], "rho": 0.6},
+        {"type": "cube", "center": [0.3, 0.3, 0.3], "side": 0.5, "rho": 0.3},
+        {"type": "sphere", "center": [-0.2, 0.1, 0.0], "radius": 0.25, "rho": -1.0},
+        {"type": "cylinder", "p0": [-0.6, -0.5, -0.4], "p1": [0.5, 0.4, 0.45], "radius": 0.08, "rho": -0.6},
+        {"type": "parallelepiped", "origin": [-0.1, -0.1, -0.1], "v0": [0.7, 0.0, 0.0], "v1": [0.1, 0.6, 0.0],
+         "v2": [0.1, 0.1, 0.5], "rho": 0.2},
+        {"type": "gyroid", "center": [0.0, 0.0, 0.0], "scale": 0.15, "thickness": 0.3, "rho": 0.1},
+    ]}
+    for greedy in (False, True):
+        o = dict(obj, greedy_dens_eval=greedy)
+        out, nref, _ = gpu_vs_oracle(X, O, o, res=40, ds=0.02)
+        assert_parity(out, nref)
+
+
+@pytest.mark.parametrize("prim", [
+    {"type": "sphere", "center": [0.1, 0.0, -0.1], "radius": 0.5, "rho": 2.0},
+    {"type": "cylinder", "p0": [0.0, 0.0, -0.7], "p1": [0.2, 0.1, 0.7], "radius": 0.2, "rho": -0.5},
+    {"type": "gyroid", "center": [0.0, 0.0, 0.0], "scale": 0.2, "thickness": 0.25, "rho": 0.5},
+], ids=lambda p: p["type"])
+def test_bare_primitive_roots_are_not_clamped(X, O, prim):
+    """A top-level primitive returns rho as is (2.0, negative ...): only collections clamp (objects.go:431-436)."""
+    out, nref, _ = gpu_vs_oracle(X, O, prim, res=32, ds=0.02 if prim["type"] != "gyroid" else 0.01, views=((90.0, 90.0),))
+    assert_parity(out, nref)
+
+
+def test_near_cancelling_collection_sum(X, O):
+    """rho values whose partial sums cancel: zero-ness of the sum decides refinement (main.go:181)."""
+    obj = {"type": "object_collection", "objects": [
+        {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.6, "rho": 0.1},
+        {"type": "sphere", "center": [0.1, 0.0, 0.0], "radius": 0.5, "rho": 0.2},
+        {"type": "sphere", "center": [0.0, 0.1, 0.0], "radius": 0.45, "rho": -0.3},
+        {"type": "box", "center": [0.0, 0.0, 0.0], "sides": [0.5, 0.5, 0.5], "rho": 0.7},
+        {"type": "box", "center": [0.1, 0.1, 0.0], "sides": [0.4, 0.4, 0.4], "rho": -0.7},
+    ]}
+    out, nref, _ = gpu_vs_oracle(X, O, obj, res=48, ds=0.02)
+    assert_parity(out, nref)
+
+
+def test_generic_interpreter_nested_scene(X, O, scenes):
+    """A collection holding a tessellation, a voxel grid and primitives: takes the generic interpreter."""
+    lat = json.loads((scenes / "pillar_array.json").read_text())
+    rng = np.random.default_rng(4)
+    vol = rng.random((6, 5, 7))
+    lat.update(xmin=-0.5, xmax=0.5, ymin=-0.5, ymax=0.5, zmin=-0.6, zmax=0.6)
+    obj = {"type": "object_collection", "objects": [
+        {"type": "sphere", "center": [0.6, 0.0, 0.0], "radius": 0.3, "rho": 0.4},
+        lat,
+        {"type": "box", "center": [-0.6, 0.1, 0.0], "sides": [0.3, 0.5, 0.7], "rho": -0.2},
+        {"type": "voxel_grid", "_array": vol * 0.2},
+    ]}
+    out, nref, _ = gpu_vs_oracle(X, O, obj, res=32, ds=0.02)
+    assert_parity(out, nref)
+    os.environ["XRAY_GENERIC_KERNEL"] = "1"  # the bundled shapes through the generic kernels must agree too
+    try:
+        out, nref, _ = gpu_vs_oracle(X, O, str(scenes / "lattice.json"), res=32)
+        assert_parity(out, nref)
+    finally:
+        del os.environ["XRAY_GENERIC_KERNEL"]
+
+
+def test_known_answers_through_the_gpu(X, O):
+    """The reference's own physics fixtures (main_test.go:326-437) as seen through a central pixel."""
+    import math
+
+    sph = {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.5, "rho": 1.0}
+    sc = X.Scene(sph)
+    cams = X.cameras_from_angles([(90.0, 90.0)], 5.0, 40.0)
+    res = 4  # pixel (2,2) is the optical axis: (i/(res/2)-1, j/(res/2)-1) = (0,0)
+    for prec in ("fp32", "fp64"):
+        img = X.render_scene(sc, cams, res, integration="simple", precision=prec, ds=0.001)
+        assert abs(float(img[0, 2, 2]) - math.exp(-1.0)) <= 2 * 0.001            # TestIntegrateSimple_SphereCenterRay
+        img = X.render_scene(sc, cams, res, integration="hierarchical", precision=prec, ds=0.05)
+        assert abs(float(img[0, 2, 2]) - math.exp(-1.0)) <= 0.05                # TestIntegrateHierarchical_SphereCenterRay
+        img = X.render_scene(sc, cams, res, integration="simple", precision=prec, ds=0.001, density_multiplier=2.0)
+        assert abs(float(img[0, 2, 2]) - math.exp(-2.0)) <= 2 * 0.001 * 2.0    # TestDensityMultiplierApplied
+    far = X.Scene({"type": "sphere", "center": [0.0, 0.0, 10.0], "radius": 0.01, "rho": 1.0})
+    for integ in ("simple", "hierarchical"):                                     # TestFlatFieldAppliedOnce
+        img = X.render_scene(far, cams, res, integration=integ, precision="fp64", ds=0.01, flat_field=1.0)
+        assert np.abs(img - math.exp(-1.0)).max() <= 1e-9
+        img = X.render_scene(far, cams, res, integration=integ, precision="fp32", ds=0.01, flat_field=1.0)
+        assert np.abs(img.astype(np.float64) - math.exp(-1.0)).max() <= 1e-7
+
+
+def test_ragged_sizes_and_mixed_cameras(X, O, scenes):
+    """Detector sizes that are not tile multiples (scalar store path) and cameras with different R / fov."""
+    obj = str(scenes / "cube_w_hole.json")
+    sc, osc = X.Scene(obj), O.OracleScene(obj)
+    ds = sc.auto_ds()
+    for res in (1, 7, 33, 50):
+        cams = X.cameras_from_angles([(77.0, 80.0)], R, FOV)
+        eye, cm = O.camera_from_angles(77.0, 80.0, R)
+        ref, _ = osc.render_view(eye, cm, res, FOV, R, ds, "hierarchical")
+        img = X.render_scene(sc, cams, res, ds=ds)
+        assert img.shape == (1, res, res)
+        assert np.abs(img[0].astype(np.float64) - ref).max() <= TOL_FP32
+    cams = (X._lib.XRayCameraParams64 * 3)()
+    specs = [(10.0, 90.0, 4.0, 40.0), (200.0, 60.0, 3.0, 50.0), (300.0, 120.0, 4.0, 30.0)]
+    for k, (az, pol, rr, fov) in enumerate(specs):
+        cams[k] = X.camera_from_angles(az, pol, rr, fov)
+    img = X.render_scene(sc, cams, 24, precision="fp64", ds=ds)
+    for k, (az, pol, rr, fov) in enumerate(specs):
+        eye, cm = O.camera_from_angles(az, pol, rr)
+        ref, _ = osc.render_view(eye, cm, 24, fov, rr, ds, "hierarchical")
+        assert np.abs(img[k] - ref).max() <= TOL_FP64
+
+
+def test_empty_scene_and_miss(X, O):
+    """Rays that miss everything, and a collection with nothing positive: image is exp(-flat_field) exactly."""
+    import math
+
+    neg = {"type": "object_collection", "objects": [{"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.5, "rho": -1.0}]}
+    cams = X.cameras_from_angles([(0.0, 90.0)], R, FOV)
+    for prec in ("fp32", "fp64"):
+        img = X.render_scene(X.Scene(neg), cams, 16, precision=prec, ds=0.02, flat_field=0.25)
+        assert np.abs(img.astype(np.float64) - math.exp(-0.25)).max() <= (1e-7 if prec == "fp32" else 1e-15)
+    empty = {"type": "object_collection", "objects": []}
+    img = X.render_scene(X.Scene(empty), cams, 8, precision="fp64", ds=0.02)
+    assert (img == 1.0).all()
+
+
+def test_error_paths_on_gpu(X, scenes):
+    sc = X.Scene(str(scenes / "cube_w_hole.json"))
+    cams = X.cameras_from_angles([(0.0, 90.0)], R, FOV)
+    with pytest.raises(X._lib.XRayError):
+        X.render_scene(sc, cams, 8, integration=7)
+    inf = X.Scene({"type": "object_collection", "objects": []})  # MinFeatureSize = +Inf -> no auto step
+    with pytest.raises(X._lib.XRayError, match="ds"):
+        X.render_scene(inf, cams, 8)
+    L = X._lib.load()
+    o = X._lib.make_opts()
+    o.struct_size = 4
+    out = np.zeros((1, 8, 8), dtype=np.float32)
+    assert L.XRayRenderSceneCUDA(sc.handle, cams, 1, 8, ctypes.byref(o), out.ctypes.data_as(ctypes.c_void_p)) == 2

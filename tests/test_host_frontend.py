@@ -1,0 +1,253 @@
+"""Host-side logic of the product, runnable without a GPU: scene / deformation file front end
+(main.go:50-120 + FromMap type rules), native scene compiler vs the oracle, camera helpers,
+output formats, and the C ABI surface (symbols, struct layouts, argument validation)."""
+import ctypes
+import json
+import math
+import re
+import struct
+import zlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+ALL = ["cube_w_hole", "balls", "box_w_pped", "pillar_array", "lattice", "gyroid_example"]
+
+
+# ---- C ABI surface ------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(X):
+    L = X._lib.load()
+    hdr = (ROOT / "include" / "xray_cuda_render.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([A-Z][A-Za-z0-9]+)\s*\(", hdr)) - {"XRAY"}
+    names = {n for n in names if n.startswith(("XRay", "Assemble", "Render"))}
+    assert len(names) >= 22
+    for n in sorted(names):
+        assert hasattr(L, n), f"libcuda_render.so does not export {n}"
+    assert set(X._lib.LEGACY_SYMBOLS) <= names and set(X._lib.EXTENDED_SYMBOLS) <= names
+
+
+def test_legacy_struct_layouts(X):
+    # SURVEY.md 8b [probe]: CylinderParams 32 B, XRayCameraParams 84 B (view@12, fov_y@76, R@80), align 4
+    C, P = X._lib.CylinderParams, X._lib.XRayCameraParams
+    assert ctypes.sizeof(C) == 32 and ctypes.alignment(C) == 4
+    assert ctypes.sizeof(P) == 84 and ctypes.alignment(P) == 4
+    assert (P.view.offset, P.fov_y.offset, P.R.offset) == (12, 76, 80)
+    assert (C.p1.offset, C.radius.offset, C.rho.offset) == (12, 24, 28)
+    assert ctypes.sizeof(X._lib.XRayCameraParams64) == 21 * 8  # eye 3 + view 16 + fov + R
+
+
+def test_opts_struct_matches_library(X):
+    o = X._lib.make_opts()
+    assert o.struct_size == ctypes.sizeof(X._lib.XRayRenderOpts)
+    assert (o.integration, o.precision, o.out_dtype) == (1, 0, 0)  # hierarchical is the reference default (main.go:39)
+    assert o.ds == -1.0 and o.density_multiplier == 1.0 and o.flat_field == 0.0
+
+
+def test_legacy_argument_validation_without_gpu(X):
+    """Error contract of cuda_backend.cu:95-101: non-zero on null pointers / bad dims, never a crash."""
+    L = X._lib.load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    vol = (ctypes.c_float * 8)()
+    out = (ctypes.c_float * 4)()
+    cam = (X._lib.XRayCameraParams * 1)()
+    assert L.RenderVolumeProjectionsCUDA(None, 2, 2, 2, cam, 1, 2, 0.1, 0.0, out) == 1
+    assert L.RenderVolumeProjectionsCUDA(vol, 2, 2, 2, None, 1, 2, 0.1, 0.0, out) == 1
+    assert L.RenderVolumeProjectionsCUDA(vol, 2, 2, 2, cam, 1, 2, 0.1, 0.0, None) == 1
+    assert L.RenderVolumeProjectionsCUDA(vol, 0, 2, 2, cam, 1, 2, 0.1, 0.0, out) == 2
+    assert L.RenderVolumeProjectionsCUDA(vol, 2, 2, 2, cam, 0, 2, 0.1, 0.0, out) == 2
+    assert L.RenderVolumeProjectionsCUDA(vol, 2, 2, 2, cam, 1, 0, 0.1, 0.0, out) == 2
+    assert L.RenderVolumeProjectionsCUDA(vol, 2, 2, 2, cam, 1, 2, 0.0, 0.0, out) == 2
+    assert L.XRayLastError() != b""
+    cyl = (X._lib.CylinderParams * 1)()
+    assert L.AssembleVoxelGridCUDA(None, 1, 4, 1.0, out) == 1
+    assert L.AssembleVoxelGridCUDA(cyl, 0, 4, 1.0, out) == 2
+    assert L.AssembleVoxelGridCUDA(cyl, 1, 0, 1.0, out) == 2
+    offs = (ctypes.c_int * 9)(*([0] * 9))
+    assert L.AssembleVoxelGridSpatialCUDA(cyl, 1, 4, 1.0, 2, None, None, 0, out) == 1
+    assert L.AssembleVoxelGridSpatialCUDA(cyl, 1, 4, 1.0, 0, offs, None, 0, out) == 2
+    bad = (ctypes.c_int * 9)(0, 1, 1, 1, 1, 1, 1, 1, 3)  # claims 3 indices, none given
+    idx = (ctypes.c_int * 1)(0)
+    assert L.AssembleVoxelGridSpatialCUDA(cyl, 1, 4, 1.0, 2, bad, idx, 1, out) == 2
+
+
+def test_scene_compile_errors(X):
+    L = X._lib.load()
+    h = ctypes.c_void_p()
+    assert L.XRaySceneCompileJSON(b'{"type":"torus"}', None, ctypes.byref(h)) != 0
+    assert b"unknown object type `torus`" in L.XRayLastError()  # objects.go:676
+    assert L.XRaySceneCompileJSON(b'{"type":"sphere","center":[0,0,0],"rho":1.0}', None, ctypes.byref(h)) != 0
+    assert b"radius is not a float64" in L.XRayLastError()
+    assert L.XRaySceneCompileJSON(b'{not json', None, ctypes.byref(h)) != 0
+    nested = {"type": "object_collection", "objects": [{"type": "object_collection", "objects": []}]}
+    assert L.XRaySceneCompileJSON(json.dumps(nested).encode(), None, ctypes.byref(h)) != 0
+    assert b"unknown object type" in L.XRayLastError()  # objects.go:407: collections cannot nest
+    ok = b'{"type":"sphere","center":[0,0,0],"radius":0.5,"rho":1.0}'
+    assert L.XRaySceneCompileJSON(ok, b'{"type":"twist"}', ctypes.byref(h)) != 0
+    assert b"unknown deformation type twist" in L.XRayLastError()
+    assert L.XRaySceneCompileJSON(ok, b'{"type":"sigmoid","amplitude":1,"center":0,"lengthscale":1,"direction":"w"}',
+                                  ctypes.byref(h)) != 0
+
+
+# ---- scene front end ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ALL)
+def test_compiled_scene_matches_oracle_on_host(X, O, scenes, name):
+    sc = X.Scene(str(scenes / f"{name}.json"))
+    osc = O.OracleScene(str(scenes / f"{name}.json"))
+    assert sc.auto_ds() == osc.auto_ds()
+    rng = np.random.default_rng(0)
+    for p in rng.uniform(-1.1, 1.1, size=(3000, 3)):
+        assert sc.density_host(*p) == osc.density(*p)
+
+
+@pytest.mark.parametrize("deform", ["deformation_sigmoid", "deformation_linear"])
+def test_compiled_deformation_matches_oracle_on_host(X, O, scenes, deform):
+    sc = X.Scene(str(scenes / "gyroid_example.json"), str(scenes / f"{deform}.json"))
+    osc = O.OracleScene(str(scenes / "gyroid_example.json"), str(scenes / f"{deform}.json"), density_multiplier=1.5)
+    rng = np.random.default_rng(1)
+    for p in rng.uniform(-1.1, 1.1, size=(3000, 3)):
+        assert sc.density_host(*p, 1.5) == osc.density(*p)
+
+
+def test_scene_bounds_are_conservative(X, O, scenes):
+    """Outside XRaySceneBounds density() must be exactly 0 (ray clipping relies on it), warps included."""
+    cases = [("cube_w_hole", None), ("lattice", None), ("gyroid_example", "deformation_sigmoid"),
+             ("cube_w_hole", "deformation_linear"), ("balls", None)]
+    rng = np.random.default_rng(2)
+    for name, d in cases:
+        dp = str(scenes / f"{d}.json") if d else None
+        sc = X.Scene(str(scenes / f"{name}.json"), dp)
+        osc = O.OracleScene(str(scenes / f"{name}.json"), dp)
+        lo, hi = (np.array(v) for v in sc.bounds())
+        pts = rng.uniform(-1.8, 1.8, size=(20000, 3))
+        outside = np.any((pts < lo) | (pts > hi), axis=1)
+        assert outside.sum() > 100
+        for p in pts[outside][:4000]:
+            assert osc.density(*p) == 0.0
+        inside_nonzero = sum(osc.density(*p) != 0.0 for p in pts[~outside][:2000])
+        assert inside_nonzero > 0
+
+
+def test_yaml_type_strictness(X, tmp_path):
+    """objects.go `.(float64)` assertions: YAML ints are rejected where the Go code asserts float64."""
+    good = tmp_path / "a.yaml"
+    good.write_text("type: sphere\ncenter: [0, 0, 0]\nradius: 0.5\nrho: 1.0\n")
+    X.Scene(str(good))
+    bad = tmp_path / "b.yaml"
+    bad.write_text("type: sphere\ncenter: [0, 0, 0]\nradius: 1\nrho: 1.0\n")
+    with pytest.raises(X.SceneError, match="radius is not a float64"):
+        X.Scene(str(bad))
+    cube_bad = tmp_path / "c.yaml"
+    cube_bad.write_text("type: cube\ncenter: [0, 0, 0]\nside: 1.5\nrho: 0.7\n")  # cube center elements must be floats
+    with pytest.raises(X.SceneError, match="center"):
+        X.Scene(str(cube_bad))
+    box_ok = tmp_path / "d.yaml"
+    box_ok.write_text("type: box\ncenter: [0, 0, 0]\nsides: [1, 2, 3]\nrho: 1\n")  # ToVec / ToFloat64 accept ints
+    assert X.Scene(str(box_ok)).min_feature_size() == pytest.approx(0.1)
+    cyl = tmp_path / "e.yaml"
+    cyl.write_text("type: cylinder\np0: [0, 0, -1]\np1: [0, 0, 1]\nradius: 0.5\n")  # rho defaults to 1.0
+    assert X.Scene(str(cyl)).density_host(0, 0, 0) == 1.0
+    sci = tmp_path / "f.yaml"
+    sci.write_text("type: sphere\ncenter: [0.0, 0.0, 0.0]\nradius: 5e-1\nrho: 1.0\n")  # yaml.v3 reads 5e-1 as a float
+    assert X.Scene(str(sci)).min_feature_size() == 0.5
+
+
+def test_extension_sniffing(X, tmp_path):  # main.go:63,97: last four characters decide
+    p = tmp_path / "scene.yml"
+    p.write_text("type: sphere\ncenter: [0.0, 0.0, 0.0]\nradius: 0.5\nrho: 1.0\n")
+    with pytest.raises(ValueError, match="Unknown file extension"):
+        X.Scene(str(p))
+    j = tmp_path / "scene.json"
+    j.write_text('{"type":"sphere","center":[0,0,0],"radius":1,"rho":1}')  # JSON numbers are always float64
+    assert X.Scene(str(j)).min_feature_size() == 1.0
+
+
+def test_unit_cell_forces_greedy_and_ignores_types(X, O):
+    # objects.go:481-487: uc.objects is parsed as a collection whatever its type says, greedy forced on
+    uc = {"objects": {"objects": [{"type": "sphere", "center": [0.5, 0.5, 0.5], "radius": 0.3, "rho": 0.8},
+                                  {"type": "sphere", "center": [0.5, 0.5, 0.5], "radius": 0.3, "rho": 0.8}]},
+          "xmin": 0.0, "xmax": 1.0, "ymin": 0.0, "ymax": 1.0, "zmin": 0.0, "zmax": 1.0}
+    t = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -2.0, "xmax": 2.0, "ymin": -2.0, "ymax": 2.0, "zmin": -2.0, "zmax": 2.0}
+    assert X.Scene(t).density_host(0.5, 0.5, 0.5) == 0.8 == O.OracleScene(t).density(0.5, 0.5, 0.5)
+    assert X.Scene(t).density_host(-0.5, 1.5, 0.5) == 0.8
+
+
+def test_voxel_raw_loader(X, O, tmp_path):
+    rng = np.random.default_rng(3)
+    for dtype, npdt in [("uint8", "<u1"), ("uint16", "<u2"), ("uint32", "<u4"), ("float32", "<f4"), ("float64", "<f8")]:
+        nx, ny, nz = 3, 4, 2
+        raw = (rng.random(nx * ny * nz) * (1.0 if "float" in dtype else 200.0)).astype(npdt)
+        f = tmp_path / f"v_{dtype}.raw"
+        raw.tofile(f)
+        scene = {"type": "voxel_grid", "path": f.name, "resolution": [nx, ny, nz], "dtype": dtype}
+        sf = tmp_path / f"v_{dtype}.json"
+        sf.write_text(json.dumps(scene))
+        sc, osc = X.Scene(str(sf)), O.OracleScene(str(sf))
+        assert sc.min_feature_size() == osc.min_feature_size() == 2.0 / 4
+        for p in rng.uniform(-1, 1, size=(200, 3)):
+            a, b = sc.density_host(*p), osc.density(*p)
+            assert a == b
+    with pytest.raises(X.SceneError, match="file size"):
+        X.voxel_grid_from_raw(str(tmp_path / "v_uint8.raw"), [5, 5, 5], "uint8")
+
+
+# ---- camera ---------------------------------------------------------------------------------
+def test_camera_matches_oracle_bitwise(X, O):
+    for az, pol, R in [(90, 90, 4), (0, 90, 4), (123.4, 70.0, 4.0), (359.0, 45.0, 3.0), (200.0, 135.0, 6.0)]:
+        cam = X.camera_from_angles(az, pol, R, 40.0)
+        eye, m = O.camera_from_angles(az, pol, R)
+        assert list(cam.eye) == list(eye)
+        assert np.array_equal(X.camera_matrix(cam), m)
+        assert cam.fov_y == 40.0 and cam.R == R
+
+
+def test_generate_camera_angles_and_sharding(X):
+    a = X.generate_camera_angles(360)
+    assert len(a) == 360 and a[0] == {"azimuthal": 90.0, "polar": 90.0} and a[1]["azimuthal"] == 91.0
+    shards = [X.generate_camera_angles(10, r, 4) for r in range(4)]  # --jobs_modulo 4 --job r
+    seen = sorted(x["azimuthal"] for s in shards for x in s)
+    assert seen == sorted(x["azimuthal"] for x in X.generate_camera_angles(10))
+    assert [len(s) for s in shards] == [3, 3, 2, 2]
+    assert X.parse_float_list("1, 2.5 ,3") == [1.0, 2.5, 3.0] and X.parse_float_list("") == []
+
+
+def test_legacy_camera_narrowing_roundtrip(X):
+    cams = X.cameras_from_angles([(37.0, 60.0)], 4.0, 40.0)
+    c32 = X.to_legacy(cams)
+    back = X.from_legacy(c32)
+    assert back[0].eye[0] == float(np.float32(cams[0].eye[0]))
+    assert back[0].view[5] == float(np.float32(cams[0].view[5]))
+    assert back[0].R == 4.0 and back[0].fov_y == 40.0
+
+
+# ---- output formats -------------------------------------------------------------------------
+def test_png_quantisation_and_orientation(X, tmp_path):
+    img = np.array([[0.0, 0.25], [0.5, 1.0]])  # img[i][j]
+    rgba = X.image_to_rgba8(img)
+    # main.go:495-498: uint16(val*0xffff) >> 8, pixel (i,j) at x=i, y=res-1-j
+    q = lambda v: int(v * 0xFFFF) >> 8
+    assert rgba[1, 0, 0] == q(0.0) and rgba[0, 0, 0] == q(0.25) and rgba[1, 1, 0] == q(0.5) and rgba[0, 1, 0] == q(1.0)
+    assert (rgba[..., 3] == 255).all()
+    t = X.image_to_rgba8(img, transparency=True)
+    assert t[0, 1, 3] == 0 and t[1, 0, 3] == 255  # alpha 0 only where val == 1 (main.go:486-492)
+    p = tmp_path / "x.png"
+    X.write_png(str(p), rgba)
+    data = p.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h, depth, ctype = struct.unpack(">IIBB", data[16:26])
+    assert (w, h, depth, ctype) == (2, 2, 8, 6)
+    idat = data[data.index(b"IDAT") + 4:data.index(b"IEND") - 8]
+    raw = zlib.decompress(idat)
+    assert raw == b"".join(b"\x00" + rgba[y].tobytes() for y in range(2))
+
+
+def test_renderer_parameter_validation(X):
+    r = X.XRayRenderer()
+    with pytest.raises(ValueError, match="'input' parameter is required"):
+        r.render({})
+    out = r.render({"input": "x.json", "ds": 0})
+    assert out["success"] is False and "ds is 0" in out["error"]  # api.go:96-98
+    out = r.render({"input": "x.json", "density_multiplier": 0})
+    assert out["success"] is False and "density_multiplier is 0" in out["error"]  # api.go:99-101

@@ -414,7 +414,7 @@ static int run_job(Job& J) {
     P.stats = J.opts.stats ? C->d_stats : nullptr;
     {
         size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
-        size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));
+        size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 5 * sizeof(float) + 8 * sizeof(unsigned int));
         size_t queue = (size_t)kQueueCap * kBlockThreads * sizeof(int);
         P.prog_in_smem = (prog + stack + queue) <= 160 * 1024 ? 1 : 0;
         P.smem_prog_bytes = P.prog_in_smem ? (unsigned int)prog : 0u;

@@ -138,10 +138,13 @@ __global__ void __launch_bounds__(kBlockThreads) render_scene_fast_kernel(const 
     SaveStack<Exact> ste;
     ste.r = reinterpret_cast<double*>(smem + P.smem_prog_bytes);
     ste.u = reinterpret_cast<unsigned int*>(ste.r + (size_t)P.scene.save_depth * 5 * blockDim.x);
-    SaveStack<Fast> stf;  // the fp32 walk is finished before the fp64 one starts: share the storage
-    stf.r = reinterpret_cast<float*>(ste.r);
-    stf.u = ste.u;
-    int* queue = reinterpret_cast<int*>(ste.u + (size_t)P.scene.save_depth * 4 * blockDim.x);
+    // The fp32 walk needs its OWN frames: another warp of this CTA may be inside the fp64 fallback
+    // while this warp still has live fp32 frames, and the [slot][thread] layouts of the two element
+    // sizes interleave.
+    SaveStack<Fast> stf;
+    stf.r = reinterpret_cast<float*>(ste.u + (size_t)P.scene.save_depth * 4 * blockDim.x);
+    stf.u = reinterpret_cast<unsigned int*>(stf.r + (size_t)P.scene.save_depth * 5 * blockDim.x);
+    int* queue = reinterpret_cast<int*>(stf.u + (size_t)P.scene.save_depth * 4 * blockDim.x);
 
     int view, i, j;
     pixel_of_thread(P, view, i, j);
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(kBlockThreads) voxelize_scene_kernel(const Ren
 size_t scene_kernel_smem_bytes(const RenderParams& P, bool with_queue) {
     size_t b = P.smem_prog_bytes;
     b += (size_t)P.scene.save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));
+    if (with_queue) b += (size_t)P.scene.save_depth * kBlockThreads * (5 * sizeof(float) + 4 * sizeof(unsigned int));
     if (with_queue) b += (size_t)kQueueCap * kBlockThreads * sizeof(int);
     return b;
 }
