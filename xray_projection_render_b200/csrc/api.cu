@@ -32,6 +32,8 @@ cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz
 cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, const unsigned char* d_nfine,
                                int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
+cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
+                                     cudaStream_t stream);
 cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
                                       const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
@@ -259,6 +261,10 @@ struct DevCtx {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     CamDev* h_cams = nullptr;  // pinned staging for the camera upload
     size_t h_cams_cap = 0;
+    // voxel volume as a layered 2D array (layers = z, width = y, height = x) for texture gather
+    cudaArray_t vol_arr = nullptr;
+    cudaTextureObject_t vol_tex = 0;
+    int vol_dims[3] = {0, 0, 0};
 };
 static std::mutex g_ctx_mu;
 static std::map<int, DevCtx*> g_ctx;
@@ -282,6 +288,11 @@ static void ctx_release(DevCtx* c) {
     if (c->d_nfine) cudaFree(c->d_nfine);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_cams) cudaFreeHost(c->h_cams);
+    if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
+    if (c->vol_arr) cudaFreeArray(c->vol_arr);
+    c->vol_tex = 0;
+    c->vol_arr = nullptr;
+    c->vol_dims[0] = c->vol_dims[1] = c->vol_dims[2] = 0;
     for (int b = 0; b < 2; ++b) {
         if (c->d_img[b]) cudaFree(c->d_img[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
@@ -412,12 +423,58 @@ static int run_job(Job& J) {
     }
     P.out_f64 = J.opts.out_dtype == XRAY_OUT_F64;
     P.stats = J.opts.stats ? C->d_stats : nullptr;
+    P.skip_m2s = getenv("XRAY_NO_SKIP") ? 0.0f : (float)(0.999 / (J.ds * std::fmax(1.0, h->warp_lipschitz)));
     {
         size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
         size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 5 * sizeof(float) + 8 * sizeof(unsigned int));
         size_t queue = (size_t)kQueueCap * kBlockThreads * sizeof(int);
         P.prog_in_smem = (prog + stack + queue) <= 160 * 1024 ? 1 : 0;
         P.smem_prog_bytes = P.prog_in_smem ? (unsigned int)prog : 0u;
+    }
+
+    // Dedicated voxel kernel: (re)fill the layered array from the linear device volume.  Falls back to the
+    // __ldg kernel when the array cannot be had (dimension limits: 2048 layers, 32768 x 32768 texels).
+    bool use_tex = false;
+    if (J.fast_volume && !getenv("XRAY_VOLUME_LDG")) {
+        const int vx = h->voxel_dims[0][0], vy = h->voxel_dims[0][1], vz = h->voxel_dims[0][2];
+        if (vz <= 2048 && vx <= 32768 && vy <= 32768) {
+            if (C->vol_dims[0] != vx || C->vol_dims[1] != vy || C->vol_dims[2] != vz) {
+                CUJ(7, cudaStreamSynchronize(stream));
+                if (C->vol_tex) cudaDestroyTextureObject(C->vol_tex);
+                if (C->vol_arr) cudaFreeArray(C->vol_arr);
+                C->vol_tex = 0;
+                C->vol_arr = nullptr;
+                C->vol_dims[0] = C->vol_dims[1] = C->vol_dims[2] = 0;
+                cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+                if (cudaMalloc3DArray(&C->vol_arr, &cd, make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz), cudaArrayLayered) == cudaSuccess) {
+                    cudaResourceDesc rd = {};
+                    rd.resType = cudaResourceTypeArray;
+                    rd.res.array.array = C->vol_arr;
+                    cudaTextureDesc td = {};
+                    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+                    td.filterMode = cudaFilterModePoint;
+                    td.readMode = cudaReadModeElementType;
+                    td.normalizedCoords = 0;
+                    if (cudaCreateTextureObject(&C->vol_tex, &rd, &td, nullptr) == cudaSuccess) {
+                        C->vol_dims[0] = vx; C->vol_dims[1] = vy; C->vol_dims[2] = vz;
+                    } else {
+                        cudaFreeArray(C->vol_arr);
+                        C->vol_arr = nullptr;
+                        C->vol_tex = 0;
+                    }
+                }
+                cudaGetLastError();
+            }
+            if (C->vol_arr) {
+                cudaMemcpy3DParms cp = {};
+                cp.srcPtr = make_cudaPitchedPtr(ds->d_vox[0], (size_t)vy * sizeof(float), (size_t)vy, (size_t)vx);
+                cp.dstArray = C->vol_arr;
+                cp.extent = make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz);
+                cp.kind = cudaMemcpyDeviceToDevice;
+                CUJ(4, cudaMemcpy3DAsync(&cp, stream));
+                use_tex = true;
+            }
+        }
     }
 
     const size_t max_batch_bytes = (size_t)256 << 20;
@@ -430,6 +487,9 @@ static int run_job(Job& J) {
         P.out = d_dst;
         // the grid is one CTA per (view, tile); keep it below 2^31
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
+        if (J.fast_volume && use_tex)
+            return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
+                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, stream);
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);

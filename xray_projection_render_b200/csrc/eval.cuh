@@ -383,6 +383,7 @@ __device__ __forceinline__ unsigned long long grid_lookup(const SceneView& S, co
     iz = max(0, min(gz - 1, iz));
     unsigned long long m = 0ull;
     if (alive) m = __ldg(S.grids + I.aux + ((size_t)iz * gy + iy) * gx + ix);
+    if (m >> 63) m = 0ull;  // empty cell: the word carries a skip distance, not a mask
     unsigned int lo = __reduce_or_sync(FULL_MASK, (unsigned int)m);
     unsigned int hi = __reduce_or_sync(FULL_MASK, (unsigned int)(m >> 32));
     return ((unsigned long long)hi << 32) | lo;

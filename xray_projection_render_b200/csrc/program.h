@@ -12,7 +12,7 @@
 namespace xr {
 
 constexpr uint32_t kMagic = 0x58524159u;  // "XRAY"
-constexpr uint32_t kVersion = 3;
+constexpr uint32_t kVersion = 4;
 constexpr int kMaxVoxelSlots = 4;
 constexpr int kMaxSaveDepth = 6;  // nested save frames (collections/tessellations inside collections)
 constexpr int kFrameWords = 8;    // real-typed words per save frame
@@ -92,6 +92,7 @@ struct Header {
     double min_feature_size;
     double aabb_lo[3], aabb_hi[3];  // world-space region outside of which density()==0
     double eps_pos;                 // position error bound assumed by the fp32 tolerances
+    double warp_lipschitz;          // object-space displacement per unit world displacement (deformation chain)
     int32_t voxel_dims[kMaxVoxelSlots][4];
 };
 

@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
         for (int d = 0; d < n_deform; ++d) Fast::deform(deform[d], x, y, z);
         bool alive = act;
         unsigned int um_lo = ~0u, um_hi = ~0u;
+        // clearance of this lane, in lattice steps, inside which density() is provably 0 (skipping):
+        // 0 unless the lane sits in an empty grid cell / outside the tessellation's outer box
+        float clear = 0.0f;
         if (SHAPE == SHAPE_TESS) {
             const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
             const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
@@ -306,9 +309,15 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
                 const int iz = min(gz - 1, (int)(rz * gf.z));
                 uint2 mk = make_uint2(0u, 0u);
                 if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
+                if (mk.y >> 31) {  // empty cell: low byte = Chebyshev distance (cells) to the nearest occupied cell
+                    clear = (float)((mk.x & 255u) - 1u) * (gF[0].w * P.skip_m2s);
+                    mk = make_uint2(0u, 0u);
+                }
                 um_lo = __reduce_or_sync(FULL_MASK, mk.x);
                 um_hi = __reduce_or_sync(FULL_MASK, mk.y);
             }
+            // outside the outer box (Chebyshev distance m > 0) nothing can be hit for m / (ds * lip) steps
+            if (act && !inside) clear = fmaxf(m - 4.0f * oc.w, 0.0f) * P.skip_m2s;
         } else if (has_grid) {
             const float4 g0 = gF[0], g1 = gF[1], gd = gF[2];
             const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
@@ -317,6 +326,10 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
             const int iz = min(gz - 1, max(0, __float2int_rd((z - g0.z) * g1.z)));
             uint2 mk = make_uint2(0u, 0u);
             if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
+            if (mk.y >> 31) {
+                clear = (float)((mk.x & 255u) - 1u) * (g0.w * P.skip_m2s);
+                mk = make_uint2(0u, 0u);
+            }
             um_lo = __reduce_or_sync(FULL_MASK, mk.x);
             um_hi = __reduce_or_sync(FULL_MASK, mk.y);
         }
@@ -349,7 +362,17 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
                 XR_KADD(rho * w);
                 prev = rho;
             }
-            ++k;
+            // Exact empty-space skipping: when no lane of the warp can meet a non-zero density within the
+            // next n steps (empty grid cells with clearance / still outside the outer box / not yet inside
+            // its clipped range), those steps would add rho*w = +0 and cannot flip (rho==0)!=(prev==0).
+            int adv = 1;
+            if ((um_lo | um_hi) == 0u) {
+                float a = rho == 0.0f ? clear : 0.0f;
+                if (!act) a = (!hit || k >= k1) ? 1.0e6f : (float)(k0 - k);
+                const int n = __reduce_min_sync(FULL_MASK, (int)fminf(a, 1.0e6f));
+                if (n >= 2) adv = n;  // steps k+1 .. k+n-1 are skipped, k+n is evaluated again
+            }
+            k += adv;
             if (INTEG == 1 && __any_sync(FULL_MASK, qn == kQueueCap)) {
                 mode = 1;
                 nf = 0;

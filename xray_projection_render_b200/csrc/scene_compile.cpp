@@ -730,8 +730,9 @@ static Box3 pull_back(Box3 b, const std::vector<Deform>& ds) {
 }
 
 // Lipschitz factor / evaluation error of the fp32 warp chain -> position error bound.
-static double deform_eps_pos(const std::vector<Deform>& ds) {
+static double deform_eps_pos(const std::vector<Deform>& ds, double* lip_out = nullptr) {
     double ep = kEpsPosBase;
+    double lip_total = 1.0;
     for (const auto& d : ds) {
         double lip = 1.0, add = 0.0;
         switch (d.type) {
@@ -769,7 +770,9 @@ static double deform_eps_pos(const std::vector<Deform>& ds) {
             }
         }
         ep = ep * lip + add;
+        lip_total *= std::fmax(lip, 1e-3);
     }
+    if (lip_out) *lip_out = lip_total;
     return ep;
 }
 
@@ -934,12 +937,14 @@ static bool child_touches_cell(const Node& k, const double* lo, const double* hi
 
 static int g_grid_max = 32;  // cells per axis cap (env XRAY_GRID_MAX)
 static int g_grid_min_children = 4;
+static double g_grid_feat_scale = 0.5;  // cell size in units of the smallest child feature (env XRAY_GRID_FEAT_SCALE)
 
 // Child-mask grid for a collection: cell -> 64-bit set of children that may be non-zero there.
 // region: where the collection is evaluated (unit-cell bounds) or null (use children extents).
 static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_t& f32_idx, uint32_t& grid_idx) {
     size_t n = coll.kids.size();
-    if ((int)n < g_grid_min_children || n > 64) return false;
+    // a unit-cell collection is worth a grid even for one child: the grid also drives empty-space skipping
+    if ((int)n < (region ? 1 : g_grid_min_children) || n > 64) return false;
     Box3 reg;
     if (region) reg = *region;
     else
@@ -965,7 +970,7 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
             default: break;
         }
     if (!std::isfinite(feat) || !(feat > 0)) feat = emax / 8;
-    double cell = std::fmax(feat, emax / g_grid_max);
+    double cell = std::fmax(feat * g_grid_feat_scale, emax / g_grid_max);
     int g[3];
     for (int i = 0; i < 3; ++i) g[i] = std::max(1, std::min(g_grid_max, (int)std::ceil(ext[i] / cell)));
     if (g[0] * g[1] * g[2] <= 1) return false;
@@ -984,8 +989,54 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
                     if (child_touches_cell(coll.kids[c], lo, hi)) m |= (uint64_t)1 << c;
                 B.grids[grid_idx + ((size_t)iz * g[1] + iy) * g[0] + ix] = m;
             }
+    // Empty cells carry a skip distance instead of a mask: bit 63 set, low byte = Chebyshev distance (in
+    // cells, >= 1, capped) to the nearest cell any child can touch; periodic when the grid tiles a unit cell.
+    // Needs bit 63 free, i.e. at most 63 children.
+    if (n <= 63) {
+        const int gx = g[0], gy = g[1], gz = g[2];
+        const size_t nc = (size_t)gx * gy * gz;
+        std::vector<int> dist(nc, -1);
+        std::vector<size_t> frontier, next;
+        for (size_t c = 0; c < nc; ++c)
+            if (B.grids[grid_idx + c] != 0) {
+                dist[c] = 0;
+                frontier.push_back(c);
+            }
+        const bool periodic = region != nullptr;
+        int d = 0;
+        while (!frontier.empty()) {
+            ++d;
+            next.clear();
+            for (size_t c : frontier) {
+                const int ix = (int)(c % gx), iy = (int)((c / gx) % gy), iz = (int)(c / ((size_t)gx * gy));
+                for (int dz = -1; dz <= 1; ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            int jx = ix + dx, jy = iy + dy, jz = iz + dz;
+                            if (periodic) {
+                                jx = (jx + gx) % gx;
+                                jy = (jy + gy) % gy;
+                                jz = (jz + gz) % gz;
+                            } else if (jx < 0 || jy < 0 || jz < 0 || jx >= gx || jy >= gy || jz >= gz) {
+                                continue;
+                            }
+                            const size_t q = ((size_t)jz * gy + jy) * gx + jx;
+                            if (dist[q] < 0) {
+                                dist[q] = d;
+                                next.push_back(q);
+                            }
+                        }
+            }
+            frontier.swap(next);
+        }
+        for (size_t c = 0; c < nc; ++c)
+            if (B.grids[grid_idx + c] == 0) {
+                const int dd = dist[c] < 0 ? 255 : std::min(dist[c], 255);
+                B.grids[grid_idx + c] = (1ull << 63) | (uint64_t)dd;
+            }
+    }
     f32_idx = B.f32_idx();
-    B.f4(reg.lo[0], reg.lo[1], reg.lo[2], 0);
+    B.f4(reg.lo[0], reg.lo[1], reg.lo[2], std::fmin(cs[0], std::fmin(cs[1], cs[2])));  // .w = smallest cell edge
     B.f4(1.0 / cs[0], 1.0 / cs[1], 1.0 / cs[2], 0);
     B.f4bits((uint32_t)g[0], (uint32_t)g[1], (uint32_t)g[2], 0);
     B.f4(g[0], g[1], g[2], 0);  // the same dims as floats (saves three I2F per sample)
@@ -1133,9 +1184,11 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static bool build_blob(XRayScene& sc, std::string& err) {
     if (const char* e = getenv("XRAY_GRID_MAX")) g_grid_max = std::max(1, std::min(64, atoi(e)));
     if (const char* e = getenv("XRAY_GRID_MIN_CHILDREN")) g_grid_min_children = std::max(1, atoi(e));
+    if (const char* e = getenv("XRAY_GRID_FEAT_SCALE")) g_grid_feat_scale = std::max(0.05, atof(e));
     Builder B;
     B.sc = &sc;
-    B.ep = deform_eps_pos(sc.deforms);
+    double warp_lip = 1.0;
+    B.ep = deform_eps_pos(sc.deforms, &warp_lip);
     if (!emit_node(B, sc.root, true, 0)) {
         err = B.err;
         return false;
@@ -1181,6 +1234,7 @@ static bool build_blob(XRayScene& sc, std::string& err) {
     h.n_voxel_slots = (uint32_t)sc.n_vox;
     h.min_feature_size = node_min_feature_size(sc.root, sc);
     h.eps_pos = B.ep;
+    h.warp_lipschitz = warp_lip;
     for (int s = 0; s < sc.n_vox; ++s) {
         h.voxel_dims[s][0] = sc.vox[s].nx;
         h.voxel_dims[s][1] = sc.vox[s].ny;
