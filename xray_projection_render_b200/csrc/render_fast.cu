@@ -84,7 +84,10 @@ __device__ __forceinline__ void emit_child(bool in, bool near, float rho, bool g
 template <bool COUNT>
 __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const float4* __restrict__ sF, int rb, int re,
                                            unsigned int cflags, bool has_mask, unsigned int umask_lo, unsigned int umask_hi,
-                                           float x, float y, float z, bool alive, bool& unc, unsigned int& prim_tests) {
+                                           float x, float y, float z, bool alive, bool& unc, unsigned int& prim_tests,
+                                           float& clr) {
+    // clr: object-space max-norm distance within which no evaluated child can change its answer
+    // (only gyroids report one; any other child tested sets it to 0)
     const bool greedy = (cflags & F_GREEDY) != 0;
     float acc = 0.0f, res = alive ? 0.0f : -1.0f;
     int nhit = 0;
@@ -105,6 +108,7 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
                 const float ac = fabsf(cc - 0.5f) - 0.5f;                     // <= 0 between the caps
                 const float worst = fmaxf(ar * t.w, ac);                      // t.w = tolc/tolr: common scale
                 const bool in = worst < -t.z;
+                clr = 0.0f;
                 emit_child(in, !in && worst < t.z, a.w, greedy, res, acc, unc, nhit);
             })
         } else if (w0.x == OP_SPHERE) {
@@ -112,12 +116,14 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
                 const float4 a = q[c * kF32Sphere], b = q[c * kF32Sphere + 1];
                 const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
                 const float m = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - b.x;
+                clr = 0.0f;
                 emit_child(m < 0.0f, fabsf(m) < b.y, a.w, greedy, res, acc, unc, nhit);
             })
         } else if (w0.x == OP_BOX) {
             XR_FOR_EACH_CHILD(lo, hi, {
                 const float4 a = q[c * kF32Box], b = q[c * kF32Box + 1];
                 const float m = fmaxf(fabsf(x - a.x) - b.x, fmaxf(fabsf(y - a.y) - b.y, fabsf(z - a.z) - b.z));
+                clr = 0.0f;
                 emit_child(m < 0.0f, fabsf(m) < b.w, a.w, greedy, res, acc, unc, nhit);
             })
         } else if (w0.x == OP_PPED) {
@@ -128,6 +134,7 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
                 const float qy = r1.x * dx + r1.y * dy + r1.z * dz;
                 const float qz = r2.x * dx + r2.y * dy + r2.z * dz;
                 const float m = fmaxf(fabsf(qx - 0.5f), fmaxf(fabsf(qy - 0.5f), fabsf(qz - 0.5f))) - 0.5f;
+                clr = 0.0f;
                 emit_child(m < 0.0f, fabsf(m) < r0.w, a.w, greedy, res, acc, unc, nhit);
             })
         } else {  // OP_GYROID
@@ -138,6 +145,7 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
                 sincosf((y - a.y) * b.x, &sy, &cy);
                 sincosf((z - a.z) * b.x, &sz, &cz);
                 const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
+                if (res == 0.0f) clr = fminf(clr, fmaxf(fabsf(t) - b.z, 0.0f) * b.w);
                 emit_child(t < 0.0f, fabsf(t) < b.z, a.w, greedy, res, acc, unc, nhit);
             })
         }
@@ -288,6 +296,7 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
         // clearance of this lane, in lattice steps, inside which density() is provably 0 (skipping):
         // 0 unless the lane sits in an empty grid cell / outside the tessellation's outer box
         float clear = 0.0f;
+        float tess_limit = 3.0e38f;  // object-space distance to the nearest unit-cell face / outer-box exit
         if (SHAPE == SHAPE_TESS) {
             const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
             const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
@@ -318,6 +327,9 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
             }
             // outside the outer box (Chebyshev distance m > 0) nothing can be hit for m / (ds * lip) steps
             if (act && !inside) clear = fmaxf(m - 4.0f * oc.w, 0.0f) * P.skip_m2s;
+            // a skip justified by a child's own margin must stay inside this period and inside the outer box
+            tess_limit = fminf(fminf(fminf(rx, 1.0f - rx) * fabsf(dd.x), fminf(ry, 1.0f - ry) * fabsf(dd.y)),
+                               fminf(fminf(rz, 1.0f - rz) * fabsf(dd.z), -m));
         } else if (has_grid) {
             const float4 g0 = gF[0], g1 = gF[1], gd = gF[2];
             const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
@@ -334,8 +346,10 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
             um_hi = __reduce_or_sync(FULL_MASK, mk.y);
         }
         float rho = 0.0f;
-        if ((um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive))
-            rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests);
+        float clr = 3.0e38f;
+        const bool evaluated = (um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive);
+        if (evaluated) rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
+        if (evaluated && !has_grid && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
         rho *= dmf;
         unc = unc && act;
         if (__any_sync(FULL_MASK, unc)) {
@@ -365,12 +379,17 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
             // Exact empty-space skipping: when no lane of the warp can meet a non-zero density within the
             // next n steps (empty grid cells with clearance / still outside the outer box / not yet inside
             // its clipped range), those steps would add rho*w = +0 and cannot flip (rho==0)!=(prev==0).
+            // The same holds inside a solid whose margin is known (gyroid |g|-t with its gradient bound):
+            // the skipped steps all return this step's rho, so they add (n-1)*rho*DS and flip nothing.
             int adv = 1;
-            if ((um_lo | um_hi) == 0u) {
-                float a = rho == 0.0f ? clear : 0.0f;
+            if ((um_lo | um_hi) == 0u || !has_grid) {
+                float a = (((um_lo | um_hi) == 0u && rho != 0.0f) || unc) ? 0.0f : clear;
                 if (!act) a = (!hit || k >= k1) ? 1.0e6f : (float)(k0 - k);
                 const int n = __reduce_min_sync(FULL_MASK, (int)fminf(a, 1.0e6f));
-                if (n >= 2) adv = n;  // steps k+1 .. k+n-1 are skipped, k+n is evaluated again
+                if (n >= 2) {  // steps k+1 .. k+n-1 are skipped, k+n is evaluated again
+                    adv = n;
+                    if (act && rho != 0.0f) XR_KADD(rho * wC * (float)(n - 1));
+                }
             }
             k += adv;
             if (INTEG == 1 && __any_sync(FULL_MASK, qn == kQueueCap)) {

@@ -875,7 +875,8 @@ static void emit_prim_params(Builder& B, const Node& n) {
             double argerr = ep / std::fabs(scale) + 3.0 * u * amax;
             double tol = 2.0 * (6.0 * (argerr + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
             B.f4(p[0], p[1], p[2], p[5]);
-            B.f4(1.0 / scale, p[4], up32(tol), 0);
+            // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
+            B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
             B.d64(p, 6, kF64Gyroid);
             break;
         }
@@ -969,7 +970,8 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
             case N_PPED: feat = std::fmin(feat, 0.5 * std::fmin(len3(k.p + 3), std::fmin(len3(k.p + 6), len3(k.p + 9)))); break;
             default: break;
         }
-    if (!std::isfinite(feat) || !(feat > 0)) feat = emax / 8;
+    if (!std::isfinite(feat)) return false;  // no bounded child: every cell would list every child
+    if (!(feat > 0)) feat = emax / 8;
     double cell = std::fmax(feat * g_grid_feat_scale, emax / g_grid_max);
     int g[3];
     for (int i = 0; i < 3; ++i) g[i] = std::max(1, std::min(g_grid_max, (int)std::ceil(ext[i] / cell)));
