@@ -198,6 +198,17 @@ struct Exact {
 // Fast fp32 evaluators with guard bands.  `near` is set when the predicate is within its
 // error bound of flipping; the caller then re-evaluates the sample with Exact.
 // ---------------------------------------------------------------------------------------
+// sin and cos through the SFU: Cody-Waite reduction to [-pi, pi] (2*pi = hi - 1.7484555e-7), then
+// MUFU.SIN / MUFU.COS (abs error 2^-21.4 / 2^-21.2 on that range).  Total error < 1e-6 for |a| < 1e4;
+// the gyroid guard band (scene_compile.cpp) budgets for it.
+__device__ __forceinline__ void fast_sincos(float a, float* s, float* c) {
+    const float k = rintf(a * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, a);
+    r = fmaf(k, 1.7484555e-7f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
 struct Fast {
     typedef float real;
     static constexpr bool kFast = true;
@@ -234,7 +245,8 @@ struct Fast {
                 break;
             case D_SIGMOID: {
                 float q = r.axis == 0 ? x : (r.axis == 1 ? y : z);
-                q += p[0] / (1.0f + expf((q - p[1]) * p[2]));  // p[2] = -1/L
+                // SFU exp and reciprocal: relative error ~1e-6 on a term bounded by |A| (budgeted in eps_pos)
+                q += __fdividef(p[0], 1.0f + __expf((q - p[1]) * p[2]));  // p[2] = -1/L
                 if (r.axis == 0) x = q;
                 else if (r.axis == 1) y = q;
                 else z = q;

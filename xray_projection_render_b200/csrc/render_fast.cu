@@ -141,9 +141,9 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
             XR_FOR_EACH_CHILD(lo, hi, {
                 const float4 a = q[c * kF32Gyroid], b = q[c * kF32Gyroid + 1];
                 float sx, cx, sy, cy, sz, cz;
-                sincosf((x - a.x) * b.x, &sx, &cx);
-                sincosf((y - a.y) * b.x, &sy, &cy);
-                sincosf((z - a.z) * b.x, &sz, &cz);
+                fast_sincos((x - a.x) * b.x, &sx, &cx);
+                fast_sincos((y - a.y) * b.x, &sy, &cy);
+                fast_sincos((z - a.z) * b.x, &sz, &cz);
                 const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
                 if (res == 0.0f) clr = fminf(clr, fmaxf(fabsf(t) - b.z, 0.0f) * b.w);
                 emit_child(t < 0.0f, fabsf(t) < b.z, a.w, greedy, res, acc, unc, nhit);

@@ -873,7 +873,8 @@ static void emit_prim_params(Builder& B, const Node& n) {
             double cmax = std::fmax(std::fabs(p[0]), std::fmax(std::fabs(p[1]), std::fabs(p[2])));
             double amax = (3.0 + cmax) / std::fabs(scale);  // |argument| bound inside the render window
             double argerr = ep / std::fabs(scale) + 3.0 * u * amax;
-            double tol = 2.0 * (6.0 * (argerr + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
+            // + 1e-6 per sin/cos: SFU evaluation after Cody-Waite reduction (eval.cuh fast_sincos)
+            double tol = 2.0 * (6.0 * (argerr + 1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
             B.f4(p[0], p[1], p[2], p[5]);
             // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
             B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
