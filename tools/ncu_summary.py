@@ -47,3 +47,20 @@ cnt = collections.Counter(int(r[ie]) for r in data)
 print("top (exec count x #instrs):")
 for v, n in sorted(cnt.items(), key=lambda x: -x[0] * x[1])[:12]:
     print(f"  exec={v:>12d} x {n:5d} -> {v*n/tot*100:5.1f}%")
+
+# ---- executed-instruction mix from the SASS page (thread-level) ----
+ith = hdr.index("Predicated-On Thread Instructions Executed")
+isrc = hdr.index("Source")
+mix = collections.Counter()
+for r in data:
+    toks = r[isrc].replace("@", " @").split()
+    op = next((t for t in toks if not t.startswith("@") and not t.startswith("!")), "?").split(".")[0]
+    mix[op] += int(r[ith])
+tot_th = sum(mix.values())
+dur_ms = float(d['gpu__time_duration.sum'][1]) if 'gpu__time_duration.sum' in d else 0.0
+flop = mix["FADD"] + mix["FMUL"] + 2 * mix["FFMA"]
+print(f"thread-instr mix (top): " + ", ".join(f"{k}={v/tot_th*100:.1f}%" for k, v in mix.most_common(14)))
+if dur_ms:
+    print(f"executed fp32 arithmetic: FFMA={mix['FFMA']:.3e} FADD={mix['FADD']:.3e} FMUL={mix['FMUL']:.3e} -> {flop/(dur_ms*1e-3)/1e12:.2f} TFLOP/s "
+          f"(FMA=2) in {dur_ms:.3f} ms; all fp32-pipe ops (incl. FSETP/FMNMX/FSEL) = "
+          f"{(mix['FFMA']+mix['FADD']+mix['FMUL']+mix['FSETP']+mix['FMNMX']+mix['FMNMX3']+mix['FSEL'])/tot_th*100:.1f}% of thread instrs")

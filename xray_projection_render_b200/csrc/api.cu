@@ -417,6 +417,9 @@ static int run_job(Job& J) {
     P.tiles_j = (res + kTileJ - 1) / kTileJ;
     P.flat_field = J.opts.flat_field;
     P.dm = J.opts.density_multiplier;
+    P.dm_f = (float)P.dm;
+    P.ds_f = (float)P.ds;
+    P.ds_fine_f = (float)P.ds_fine;
     for (int a = 0; a < 3; ++a) {
         P.aabb_lo[a] = h->aabb_lo[a];
         P.aabb_hi[a] = h->aabb_hi[a];

@@ -52,6 +52,7 @@ struct RenderParams {
     int prog_in_smem;           // stage instr + fp32 pool in shared memory
     unsigned int smem_prog_bytes;
     unsigned long long* stats;  // device, XRAY_NUM_STATS counters or null
+    float dm_f, ds_f, ds_fine_f;  // fp32 copies for the hot loop (no F2F per iteration)
     float skip_m2s;             // object-space clearance -> number of lattice steps that stay inside it (0 disables skipping)
 };
 

@@ -160,7 +160,7 @@ finish:
 }
 
 template <int SHAPE, int INTEG, bool COUNT>
-__global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
+__global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
                                                                        int i_coll, int i_tess) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles] [queue kQueueCap x nt ints]
@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
     const int n_deform = P.scene.n_deform;
     const DeformRec* __restrict__ deform = P.scene.deform;
 
-    const float dmf = (float)P.dm;
-    const float dsf = (float)P.ds_fine;
+    const float dmf = P.dm_f;
+    const float dsf = P.ds_fine_f;
     // T - flat_field = sum rho*w, w = DS for plain coarse steps and ds for refined ones; Kahan
     // compensated so the fp32 sum stays ~1e-7 relative however many steps a ray takes
-    const float wC = (float)P.ds, wF = (float)P.ds_fine;
+    const float wC = P.ds_f, wF = P.ds_fine_f;
     float accT = 0.0f, cmpT = 0.0f;
 #define XR_KADD(V)                         \
     do {                                   \
@@ -328,8 +328,9 @@ __global__ void __launch_bounds__(kBlockThreads, 6) render_fast_kernel(const Ren
             // outside the outer box (Chebyshev distance m > 0) nothing can be hit for m / (ds * lip) steps
             if (act && !inside) clear = fmaxf(m - 4.0f * oc.w, 0.0f) * P.skip_m2s;
             // a skip justified by a child's own margin must stay inside this period and inside the outer box
-            tess_limit = fminf(fminf(fminf(rx, 1.0f - rx) * fabsf(dd.x), fminf(ry, 1.0f - ry) * fabsf(dd.y)),
-                               fminf(fminf(rz, 1.0f - rz) * fabsf(dd.z), -m));
+            if (!has_grid)
+                tess_limit = fminf(fminf(fminf(rx, 1.0f - rx) * fabsf(dd.x), fminf(ry, 1.0f - ry) * fabsf(dd.y)),
+                                   fminf(fminf(rz, 1.0f - rz) * fabsf(dd.z), -m));
         } else if (has_grid) {
             const float4 g0 = gF[0], g1 = gF[1], gd = gF[2];
             const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
