@@ -188,6 +188,45 @@ def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
             "sample": desc, "seconds": dt}
 
 
+def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, device_index):
+    """Second comparator of BASELINE.md: the reference's own CUDA plugin (cuda_backend.cu built unmodified for
+    sm_100 into oracle/_ref/ by oracle/Makefile), driven through the same legacy call with the same host
+    buffers.  Speed only: its images follow the half-voxel texture convention (cuda_test.go:33-40)."""
+    lib_path = ROOT / "oracle" / "_ref" / "libcuda_render_ref.so"
+    if not lib_path.exists():
+        return {"unavailable": "oracle/_ref/libcuda_render_ref.so not built (needs /root/reference at build time)"}
+    try:
+        ref = ctypes.CDLL(str(lib_path), mode=os.RTLD_LAZY | os.RTLD_LOCAL)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ref.RenderVolumeProjectionsCUDA.restype = ctypes.c_int
+        ref.RenderVolumeProjectionsCUDA.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.POINTER(X._lib.XRayCameraParams), ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_float, ctypes.c_float, fp]
+        cams32 = X.to_legacy(cams)
+        n = len(cams32)
+        nz, nx, ny = vol_np.shape
+        out = np.empty((n, res, res), dtype=np.float32)
+        ours = np.empty((n, res, res), dtype=np.float32)
+        args = (vol_np.ctypes.data_as(fp), nx, ny, nz, cams32, n, res, ctypes.c_float(ds), ctypes.c_float(0.0))
+        rc = ref.RenderVolumeProjectionsCUDA(*args, out.ctypes.data_as(fp))  # warm-up (context, allocations)
+        if rc != 0:
+            return {"unavailable": f"reference plugin returned {rc}"}
+        t0 = time.perf_counter()
+        ref.RenderVolumeProjectionsCUDA(*args, out.ctypes.data_as(fp))
+        t_ref = time.perf_counter() - t0
+        X.render_volume_legacy(vol_np, cams32, res, float(np.float32(ds)), out=ours)
+        t0 = time.perf_counter()
+        X.render_volume_legacy(vol_np, cams32, res, float(np.float32(ds)), out=ours)
+        t_ours = time.perf_counter() - t0
+        return {"what": "reference cuda_backend.cu (sm_100 build) vs this library, same RenderVolumeProjectionsCUDA call, host buffers",
+                "reference_s": t_ref, "ours_s": t_ours, "reference_gsamples_per_s": ref_samples_per_step / t_ref / 1e9,
+                "ours_gsamples_per_s": ref_samples_per_step / t_ours / 1e9, "speedup": t_ref / t_ours,
+                "max_abs_image_diff": float(np.abs(out - ours).max()),
+                "note": "image difference is the reference kernel's half-voxel texture convention, not an error of either"}
+    except OSError as exc:
+        return {"unavailable": str(exc)}
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the path (C++ restatement of the Go
     code, all host threads) on the same workload/metric.  Rank 0 only."""
@@ -379,6 +418,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "roofline": roof,
         "wall_s_timed_region": t_wall,
     }
+    if is_volume and world == 1 and not args.no_ref_cuda:
+        line["reference_cuda"] = time_reference_cuda_plugin(X, vol_np, cams, res, ds_v, ref_samples / args.steps, local_rank)
     if world == 1 and not args.no_cpu:
         cb = cpu_baseline(args.workload, budget_s=args.cpu_budget)
         line["cpu_baseline"] = {"value": cb["gsamples_per_s"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": cb["kind"],
@@ -398,6 +439,7 @@ def main():
     ap.add_argument("--volume-n", type=int, default=1024)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA plugin (voxel workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -96,7 +96,10 @@ static void free_dev_scene(DevScene& ds) {
 
 // Upload (or reuse) the program and voxel data on the current device.
 // borrowed_vox: optional device pointer to use for slot 0 instead of host data.
-static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const void* borrowed_vox, DevScene** out) {
+// peer_dev >= 0: voxel data that needs (re)loading is pulled from that device's copy over NVLink
+// (cudaMemcpyPeerAsync) instead of another H2D of the caller's buffer.
+static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const void* borrowed_vox, DevScene** out,
+                            int peer_dev = -1) {
     SceneCache* c = cache_of(sc);
     std::lock_guard<std::mutex> lk(c->mu);
     DevScene& ds = c->per_dev[dev];
@@ -129,7 +132,15 @@ static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const v
                 if (ds.vox_borrowed[s]) ds.d_vox[s] = nullptr;
                 ds.vox_borrowed[s] = false;
                 if (!ds.d_vox[s]) CU(3, cudaMalloc(&ds.d_vox[s], bytes));
-                CU(4, cudaMemcpyAsync(ds.d_vox[s], vh.data, bytes, cudaMemcpyHostToDevice, stream));
+                const DevScene* src = nullptr;
+                if (peer_dev >= 0 && peer_dev != dev) {
+                    auto it = c->per_dev.find(peer_dev);
+                    if (it != c->per_dev.end() && it->second.d_vox[s] && it->second.vox_version[s] == vh.version &&
+                        it->second.vox_bytes[s] == bytes)
+                        src = &it->second;
+                }
+                if (src) CU(4, cudaMemcpyPeerAsync(ds.d_vox[s], dev, src->d_vox[s], peer_dev, bytes, stream));
+                else CU(4, cudaMemcpyAsync(ds.d_vox[s], vh.data, bytes, cudaMemcpyHostToDevice, stream));
                 ds.vox_bytes[s] = bytes;
                 ds.vox_version[s] = vh.version;
             }
@@ -233,6 +244,7 @@ struct Job {
     bool use_user_stream;
     const void* borrowed_vox;
     bool fast_volume;  // dedicated voxel kernel (single voxel_grid root, fp32, simple, no warp)
+    int peer_dev;      // device already holding the voxel data (multi-GPU replication), or -1
     unsigned long long stats[XRAY_NUM_STATS];
     int rc;
     std::string err;
@@ -333,7 +345,7 @@ static int run_job(Job& J) {
     RenderParams P = {};
 
     DevScene* ds = nullptr;
-    rc = ensure_dev_scene(J.scene, J.dev, stream, J.borrowed_vox, &ds);
+    rc = ensure_dev_scene(J.scene, J.dev, stream, J.borrowed_vox, &ds, J.peer_dev);
     if (rc) {
         J.err = g_last_error;
         return rc;
@@ -632,6 +644,31 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
     }
     const int G = (int)devs.size();
 
+    // Multi-GPU with host voxel data: upload once to the first device, the others pull it over NVLink.
+    int replicated_from = -1;
+    if (G > 1 && h->n_voxel_slots > 0 && !borrowed_vox) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (int a = 0; a < G; ++a)
+            for (int b = 0; b < G; ++b)
+                if (a != b) {
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, devs[a], devs[b]) == cudaSuccess && can) {
+                        cudaSetDevice(devs[a]);
+                        cudaDeviceEnablePeerAccess(devs[b], 0);  // "already enabled" is fine
+                        cudaGetLastError();
+                    }
+                }
+        CU(3, cudaSetDevice(devs[0]));
+        DevScene* ds0 = nullptr;
+        if (int rc = ensure_dev_scene(scene, devs[0], 0, nullptr, &ds0)) {
+            cudaSetDevice(cur);
+            return rc;
+        }
+        replicated_from = devs[0];
+        cudaSetDevice(cur);
+    }
+
     // group views by R (the sample lattice depends on R), then shard each group modulo G
     std::vector<double> Rs;
     for (int v = 0; v < n; ++v)
@@ -655,6 +692,7 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
             J.use_user_stream = out_on_device;
             J.borrowed_vox = borrowed_vox;
             J.fast_volume = fast_volume;
+            J.peer_dev = replicated_from;
             memset(J.stats, 0, sizeof(J.stats));
             J.rc = 0;
         }
