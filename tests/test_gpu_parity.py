@@ -200,3 +200,65 @@ def test_error_paths_on_gpu(X, scenes):
     o.struct_size = 4
     out = np.zeros((1, 8, 8), dtype=np.float32)
     assert L.XRayRenderSceneCUDA(sc.handle, cams, 1, 8, ctypes.byref(o), out.ctypes.data_as(ctypes.c_void_p)) == 2
+
+
+def _foam(n_cells, rad, jitter=0.0):
+    """Explicit object_collection of a Kelvin foam (objects.go:588-637 strut table), n_cells^3 cells in [-0.8, 0.8]^3."""
+    from test_oracle_known_answers import kelvin
+
+    size = 1.6 / n_cells
+    uc = kelvin(rad, size)["objects"]["objects"]
+    rng = np.random.default_rng(8)
+    objs = []
+    for a in range(n_cells):
+        for b in range(n_cells):
+            for c in range(n_cells):
+                off = np.array([a, b, c]) * size - 0.8
+                for o in uc:
+                    objs.append({"type": "cylinder", "p0": list(np.array(o["p0"]) + off + rng.normal(0, jitter, 3)),
+                                 "p1": list(np.array(o["p1"]) + off + rng.normal(0, jitter, 3)), "radius": rad,
+                                 "rho": float(rng.choice([1.0, 0.6, -0.4])) if jitter else 1.0})
+    return objs
+
+
+@pytest.mark.parametrize("greedy", [False, True])
+def test_big_collections_use_cell_lists(X, O, greedy):
+    """More than 63 children: no 64-bit child mask; per-cell ascending child lists merged across the warp keep
+    the reference's summation / greedy order (objects.go:422-438).  Mixed-sign rho makes order matter."""
+    objs = _foam(2, 0.03, jitter=0.01) + [{"type": "sphere", "center": [0.1, 0.0, -0.2], "radius": 0.25, "rho": 0.5},
+                                           {"type": "box", "center": [-0.3, 0.2, 0.3], "sides": [0.3, 0.2, 0.4], "rho": -0.7}]
+    obj = {"type": "object_collection", "objects": objs, "greedy_dens_eval": greedy}
+    out, nref, _ = gpu_vs_oracle(X, O, obj, res=32, ds=0.01, views=((100.0, 80.0), (10.0, 95.0)))
+    assert_parity(out, nref)
+    # the lists really are in use: far fewer primitive tests than brute force
+    assert out["fp32"][1]["primitive_tests"] < 0.05 * out["fp32"][1]["evaluated_samples"] * len(objs)
+
+
+def test_big_unit_cell_collection(X, O):
+    """A tessellated unit cell with > 63 struts (cell lists under the periodic fold + skip distances)."""
+    uc_objs = _foam(2, 0.02)
+    for o in uc_objs:  # move the foam into a [0, 1.6]^3 unit cell
+        o["p0"] = [v + 0.8 for v in o["p0"]]
+        o["p1"] = [v + 0.8 for v in o["p1"]]
+    uc = {"objects": {"objects": uc_objs}, "xmin": 0.0, "xmax": 1.6, "ymin": 0.0, "ymax": 1.6, "zmin": 0.0, "zmax": 1.6}
+    obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.9, "xmax": 0.9, "ymin": -0.9, "ymax": 0.9, "zmin": -0.9, "zmax": 0.9}
+    out, nref, _ = gpu_vs_oracle(X, O, obj, res=32, ds=0.01, views=((200.0, 70.0),))
+    assert_parity(out, nref)
+
+
+def test_skipping_changes_nothing(X, scenes):
+    """Empty-space / in-wall skipping must be invisible: same images (to fp32 summation order), same
+    reference-equivalent sample counts, fewer evaluated samples."""
+    for name, deform in (("lattice", None), ("pillar_array", None), ("gyroid_example", "deformation_sigmoid")):
+        sc = X.Scene(str(scenes / f"{name}.json"), str(scenes / f"{deform}.json") if deform else None)
+        cams = X.cameras_from_angles([(33.0, 90.0), (140.0, 70.0)], R, FOV)
+        ds = 0.004 if name == "gyroid_example" else -1.0
+        a, sa = X.render_scene(sc, cams, 96, ds=ds, return_stats=True)
+        os.environ["XRAY_NO_SKIP"] = "1"
+        try:
+            b, sb = X.render_scene(sc, cams, 96, ds=ds, return_stats=True)
+        finally:
+            del os.environ["XRAY_NO_SKIP"]
+        assert np.abs(a.astype(np.float64) - b).max() <= 2e-6
+        assert sa["ref_samples"] == sb["ref_samples"]
+        assert sa["evaluated_samples"] < sb["evaluated_samples"]

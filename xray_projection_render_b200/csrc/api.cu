@@ -29,7 +29,7 @@ namespace xr {
 cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream);
 cudaError_t launch_voxelize_scene(const RenderParams& P, int res, float* d_out, cudaStream_t stream);
 cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream);
-cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, const unsigned char* d_nfine,
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, const unsigned char* d_nfine,
                                int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
@@ -492,6 +492,17 @@ static int run_job(Job& J) {
         }
     }
 
+    // big collections carry a cell-list grid: their fp32 pool stays in global memory (only instructions are staged)
+    bool use_list = false;
+    if (shape != 0) {
+        const Instr* I = (const Instr*)(J.scene->blob.data() + h->instr_off);
+        use_list = I[i_coll].op == OP_COLL_BEGIN && (I[i_coll].flags & F_HAS_LIST);
+        if (use_list && J.opts.precision == XRAY_PRECISION_FP32) {
+            P.prog_in_smem = 0;
+            P.smem_prog_bytes = (unsigned int)((size_t)h->n_instr * sizeof(Instr));
+        }
+    }
+
     const size_t max_batch_bytes = (size_t)256 << 20;
     int max_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nv, max_batch_bytes / img_bytes));
     unsigned long long n_launches = 0;
@@ -508,8 +519,8 @@ static int run_job(Job& J) {
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
-        if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && P.prog_in_smem && fast_kernel_smem_bytes(P) <= 200 * 1024)
-            return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, C->d_nfine, i_coll, i_tess, stream);
+        if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && (P.prog_in_smem || use_list) && fast_kernel_smem_bytes(P) <= 200 * 1024)
+            return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, use_list, C->d_nfine, i_coll, i_tess, stream);
         return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
     };
 

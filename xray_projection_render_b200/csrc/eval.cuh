@@ -509,6 +509,64 @@ __device__ typename P::real eval_scene(const SceneView& S, typename P::real x, t
                 has_mask = false;
                 umask = ~0ull;
                 bool skip = !__any_sync(FULL_MASK, act);
+                if (!skip && (I.flags & F_HAS_LIST)) {
+                    // big collection: merge the lanes' ascending cell lists (see render_fast.cu eval_list);
+                    // the runs that follow are skipped
+                    const float4* g = S.f32 + I.f32_idx;
+                    const float4 gmin = g[0], ic = g[1], dims = g[2];
+                    const uint4 lb = *reinterpret_cast<const uint4*>(g + 4);
+                    const unsigned int lb64 = reinterpret_cast<const uint4*>(g + 5)->x;
+                    const unsigned long long* gbase = S.grids + I.aux;
+                    const unsigned int* l_off = reinterpret_cast<const unsigned int*>(gbase + lb.x);
+                    const unsigned short* l_idx = reinterpret_cast<const unsigned short*>(gbase + lb.z);
+                    const unsigned int* l_tab = reinterpret_cast<const unsigned int*>(gbase + lb.w);
+                    const unsigned int* l_tab64 = reinterpret_cast<const unsigned int*>(gbase + lb64);
+                    const int gx = __float_as_int(dims.x), gy = __float_as_int(dims.y), gz = __float_as_int(dims.z);
+                    const int ix = max(0, min(gx - 1, __float2int_rd(((float)x - gmin.x) * ic.x)));
+                    const int iy = max(0, min(gy - 1, __float2int_rd(((float)y - gmin.y) * ic.y)));
+                    const int iz = max(0, min(gz - 1, __float2int_rd(((float)z - gmin.z) * ic.z)));
+                    const unsigned int cell = (unsigned int)((iz * gy + iy) * gx + ix);
+                    unsigned int lp = 0u, le = 0u;
+                    if (act) {
+                        lp = __ldg(l_off + cell);
+                        le = __ldg(l_off + cell + 1);
+                    }
+                    for (;;) {
+                        const unsigned int mine = lp < le ? (unsigned int)__ldg(l_idx + lp) : 0xFFFFu;
+                        const unsigned int c = __reduce_min_sync(FULL_MASK, mine);
+                        if (c == 0xFFFFu) break;
+                        if (greedy && !__any_sync(FULL_MASK, alive && !done)) break;
+                        if (mine == c) ++lp;
+                        const unsigned int t = __ldg(l_tab + c);
+                        Instr J = I;
+                        J.f32_idx = t & 0xFFFFFFu;
+                        J.f64_idx = __ldg(l_tab64 + c);
+                        real rho;
+                        bool near = false, in;
+                        switch (t >> 24) {
+                            case OP_SPHERE: in = P::sphere(S, J, 0, x, y, z, rho, near); break;
+                            case OP_BOX: in = P::box(S, J, 0, x, y, z, rho, near); break;
+                            case OP_CYL: in = P::cyl(S, J, 0, x, y, z, rho, near); break;
+                            case OP_PPED: in = P::pped(S, J, 0, x, y, z, rho, near); break;
+                            default: in = P::gyroid(S, J, 0, x, y, z, rho, near); break;
+                        }
+                        if (alive && !done) {
+                            cnt.prim_tests++;
+                            if (P::kFast && near) unc = true;
+                            if (in) {
+                                if (greedy && rho > (real)0) {
+                                    res = rho;
+                                    done = true;
+                                } else {
+                                    multi = multi || had;
+                                    had = true;
+                                    acc += rho;
+                                }
+                            }
+                        }
+                    }
+                    skip = true;  // children handled: go straight to COLL_END
+                }
                 if (!skip && (I.flags & F_HAS_GRID)) {
                     umask = grid_lookup<P>(S, I, x, y, z, act);
                     has_mask = true;

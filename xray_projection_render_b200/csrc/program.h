@@ -35,6 +35,7 @@ enum InstrFlags : uint32_t {
     F_GREEDY = 1,    // ObjectCollection.GreedyDensEval
     F_NOSAVE = 2,    // frame needs no save/restore (it is the only thing its parent evaluates)
     F_HAS_GRID = 4,  // collection has a child-mask grid
+    F_HAS_LIST = 8,  // collection (> 63 primitive children) has a cell-list grid: per cell an ascending child list
 };
 
 // 32 bytes.  Primitive ops are "runs": n consecutive children of the same type.
@@ -57,7 +58,9 @@ struct Instr {
 //   gyroid   f32: {c,rho} {inv_scale,thickness,tol,-}                    f64: c(3),scale,thickness,rho
 //   voxel    f32: {tol,-,-,-}                                            f64: (none)
 //   tess     f32: {oc,tol_o} {oh,-} {ucmin,-} {d,-} {inv_d,tolq}         f64: outer(6: xmin,xmax,..), uc(6)
-//   grid     f32: {gmin,-} {inv_cell,-} {gx,gy,gz (as int bits), -} {outside_mask lo, hi (bits), -, -}
+//   grid     f32: {gmin,cs_min} {inv_cell,-} {gx,gy,gz (int bits), -} {gx,gy,gz as floats, -}
+//   list grid (F_HAS_LIST) adds a 5th float4 of int bits: u64 offsets (relative to Instr.aux) of
+//            cell_off[ncell+1] (u32), cell_dist[ncell] (u8), idx[] (u16), child_tab[n] (u32 = op<<24 | float4 index)
 constexpr int kF32Sphere = 2, kF32Box = 2, kF32Cyl = 3, kF32Pped = 4, kF32Gyroid = 2, kF32Voxel = 1, kF32Tess = 5,
               kF32Grid = 4;
 constexpr int kF64Sphere = 6, kF64Box = 8, kF64Cyl = 8, kF64Pped = 14, kF64Gyroid = 6, kF64Tess = 12;

@@ -66,6 +66,60 @@ __device__ __forceinline__ void emit_child(bool in, bool near, float rho, bool g
     }
 }
 
+// ---- primitive tests: `in` = surely inside, `near` = within the guard band (fp64 decides) ----
+__device__ __forceinline__ void prim_cyl(const float4* __restrict__ q, float x, float y, float z, bool& in, bool& near, float& rho) {
+    const float4 a = q[0], v = q[1], t = q[2];
+    const float wx = x - a.x, wy = y - a.y, wz = z - a.z;
+    const float cc = (wx * v.x + wy * v.y + wz * v.z) * v.w;
+    const float ex = fmaf(-v.x, cc, wx), ey = fmaf(-v.y, cc, wy), ez = fmaf(-v.z, cc, wz);
+    const float ar = fmaf(ex, ex, fmaf(ey, ey, ez * ez)) - t.x;  // < 0 inside the radius
+    const float ac = fabsf(cc - 0.5f) - 0.5f;                     // <= 0 between the caps
+    const float worst = fmaxf(ar * t.w, ac);                      // t.w = tolc/tolr: common scale
+    in = worst < -t.z;
+    near = !in && worst < t.z;
+    rho = a.w;
+}
+__device__ __forceinline__ void prim_sphere(const float4* __restrict__ q, float x, float y, float z, bool& in, bool& near, float& rho) {
+    const float4 a = q[0], b = q[1];
+    const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
+    const float m = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - b.x;
+    in = m < 0.0f;
+    near = fabsf(m) < b.y;
+    rho = a.w;
+}
+__device__ __forceinline__ void prim_box(const float4* __restrict__ q, float x, float y, float z, bool& in, bool& near, float& rho) {
+    const float4 a = q[0], b = q[1];
+    const float m = fmaxf(fabsf(x - a.x) - b.x, fmaxf(fabsf(y - a.y) - b.y, fabsf(z - a.z) - b.z));
+    in = m < 0.0f;
+    near = fabsf(m) < b.w;
+    rho = a.w;
+}
+__device__ __forceinline__ void prim_pped(const float4* __restrict__ q, float x, float y, float z, bool& in, bool& near, float& rho) {
+    const float4 a = q[0], r0 = q[1], r1 = q[2], r2 = q[3];
+    const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
+    const float qx = r0.x * dx + r0.y * dy + r0.z * dz;
+    const float qy = r1.x * dx + r1.y * dy + r1.z * dz;
+    const float qz = r2.x * dx + r2.y * dy + r2.z * dz;
+    const float m = fmaxf(fabsf(qx - 0.5f), fmaxf(fabsf(qy - 0.5f), fabsf(qz - 0.5f))) - 0.5f;
+    in = m < 0.0f;
+    near = fabsf(m) < r0.w;
+    rho = a.w;
+}
+// margin: object-space max-norm distance over which this gyroid's answer cannot change
+__device__ __forceinline__ void prim_gyroid(const float4* __restrict__ q, float x, float y, float z, bool& in, bool& near, float& rho,
+                                            float& margin) {
+    const float4 a = q[0], b = q[1];
+    float sx, cx, sy, cy, sz, cz;
+    fast_sincos((x - a.x) * b.x, &sx, &cx);
+    fast_sincos((y - a.y) * b.x, &sy, &cy);
+    fast_sincos((z - a.z) * b.x, &sz, &cz);
+    const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
+    in = t < 0.0f;
+    near = fabsf(t) < b.z;
+    rho = a.w;
+    margin = fmaxf(fabsf(t) - b.z, 0.0f) * b.w;
+}
+
 // Visit the set bits of a run's 64-bit child mask as two 32-bit words (cheap FLO/LOP3 per child).
 #define XR_FOR_EACH_CHILD(LO, HI, ...)                                      \
     for (int half_ = 0; half_ < 2; ++half_) {                                \
@@ -76,7 +130,10 @@ __device__ __forceinline__ void emit_child(bool in, bool near, float rho, bool g
             w_ &= w_ - 1;                                                    \
             if (greedy && !__any_sync(FULL_MASK, res == 0.0f)) goto finish;  \
             if (COUNT) prim_tests += (res == 0.0f) ? 1u : 0u;                \
+            bool in, near;                                                   \
+            float rho;                                                       \
             __VA_ARGS__                                                      \
+            emit_child(in, near, rho, greedy, res, acc, unc, nhit);          \
         }                                                                    \
     }
 
@@ -99,54 +156,18 @@ __device__ __forceinline__ float eval_runs(const Instr* __restrict__ sI, const f
         const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
         const float4* __restrict__ q = sF + f32_idx;
         if (w0.x == OP_CYL) {
-            XR_FOR_EACH_CHILD(lo, hi, {
-                const float4 a = q[c * kF32Cyl], v = q[c * kF32Cyl + 1], t = q[c * kF32Cyl + 2];
-                const float wx = x - a.x, wy = y - a.y, wz = z - a.z;
-                const float cc = (wx * v.x + wy * v.y + wz * v.z) * v.w;
-                const float ex = fmaf(-v.x, cc, wx), ey = fmaf(-v.y, cc, wy), ez = fmaf(-v.z, cc, wz);
-                const float ar = fmaf(ex, ex, fmaf(ey, ey, ez * ez)) - t.x;  // < 0 inside the radius
-                const float ac = fabsf(cc - 0.5f) - 0.5f;                     // <= 0 between the caps
-                const float worst = fmaxf(ar * t.w, ac);                      // t.w = tolc/tolr: common scale
-                const bool in = worst < -t.z;
-                clr = 0.0f;
-                emit_child(in, !in && worst < t.z, a.w, greedy, res, acc, unc, nhit);
-            })
+            XR_FOR_EACH_CHILD(lo, hi, { prim_cyl(q + c * kF32Cyl, x, y, z, in, near, rho); clr = 0.0f; })
         } else if (w0.x == OP_SPHERE) {
-            XR_FOR_EACH_CHILD(lo, hi, {
-                const float4 a = q[c * kF32Sphere], b = q[c * kF32Sphere + 1];
-                const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
-                const float m = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) - b.x;
-                clr = 0.0f;
-                emit_child(m < 0.0f, fabsf(m) < b.y, a.w, greedy, res, acc, unc, nhit);
-            })
+            XR_FOR_EACH_CHILD(lo, hi, { prim_sphere(q + c * kF32Sphere, x, y, z, in, near, rho); clr = 0.0f; })
         } else if (w0.x == OP_BOX) {
-            XR_FOR_EACH_CHILD(lo, hi, {
-                const float4 a = q[c * kF32Box], b = q[c * kF32Box + 1];
-                const float m = fmaxf(fabsf(x - a.x) - b.x, fmaxf(fabsf(y - a.y) - b.y, fabsf(z - a.z) - b.z));
-                clr = 0.0f;
-                emit_child(m < 0.0f, fabsf(m) < b.w, a.w, greedy, res, acc, unc, nhit);
-            })
+            XR_FOR_EACH_CHILD(lo, hi, { prim_box(q + c * kF32Box, x, y, z, in, near, rho); clr = 0.0f; })
         } else if (w0.x == OP_PPED) {
-            XR_FOR_EACH_CHILD(lo, hi, {
-                const float4 a = q[c * kF32Pped], r0 = q[c * kF32Pped + 1], r1 = q[c * kF32Pped + 2], r2 = q[c * kF32Pped + 3];
-                const float dx = x - a.x, dy = y - a.y, dz = z - a.z;
-                const float qx = r0.x * dx + r0.y * dy + r0.z * dz;
-                const float qy = r1.x * dx + r1.y * dy + r1.z * dz;
-                const float qz = r2.x * dx + r2.y * dy + r2.z * dz;
-                const float m = fmaxf(fabsf(qx - 0.5f), fmaxf(fabsf(qy - 0.5f), fabsf(qz - 0.5f))) - 0.5f;
-                clr = 0.0f;
-                emit_child(m < 0.0f, fabsf(m) < r0.w, a.w, greedy, res, acc, unc, nhit);
-            })
+            XR_FOR_EACH_CHILD(lo, hi, { prim_pped(q + c * kF32Pped, x, y, z, in, near, rho); clr = 0.0f; })
         } else {  // OP_GYROID
             XR_FOR_EACH_CHILD(lo, hi, {
-                const float4 a = q[c * kF32Gyroid], b = q[c * kF32Gyroid + 1];
-                float sx, cx, sy, cy, sz, cz;
-                fast_sincos((x - a.x) * b.x, &sx, &cx);
-                fast_sincos((y - a.y) * b.x, &sy, &cy);
-                fast_sincos((z - a.z) * b.x, &sz, &cz);
-                const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
-                if (res == 0.0f) clr = fminf(clr, fmaxf(fabsf(t) - b.z, 0.0f) * b.w);
-                emit_child(t < 0.0f, fabsf(t) < b.z, a.w, greedy, res, acc, unc, nhit);
+                float margin;
+                prim_gyroid(q + c * kF32Gyroid, x, y, z, in, near, rho, margin);
+                if (res == 0.0f) clr = fminf(clr, margin);
             })
         }
     }
@@ -159,13 +180,51 @@ finish:
     return val;
 }
 
-template <int SHAPE, int INTEG, bool COUNT>
+// Big collections (> 63 primitive children): every lane owns the ascending child list [lp, le) of its grid
+// cell; a warp min-reduction merges the lists, so the union is visited in child order and each candidate
+// is tested once by the whole warp (parameters through __ldg: uniform address, one L1 sector).
+template <bool COUNT>
+__device__ __forceinline__ float eval_list(const float4* __restrict__ F, const unsigned int* __restrict__ tab,
+                                           const unsigned short* __restrict__ idx, unsigned int lp, unsigned int le,
+                                           unsigned int cflags, float x, float y, float z, bool alive, bool& unc,
+                                           unsigned int& prim_tests) {
+    const bool greedy = (cflags & F_GREEDY) != 0;
+    float acc = 0.0f, res = alive ? 0.0f : -1.0f;
+    int nhit = 0;
+    for (;;) {
+        const unsigned int mine = lp < le ? (unsigned int)__ldg(idx + lp) : 0xFFFFu;
+        const unsigned int c = __reduce_min_sync(FULL_MASK, mine);
+        if (c == 0xFFFFu) break;
+        if (greedy && !__any_sync(FULL_MASK, res == 0.0f)) break;
+        if (mine == c) ++lp;
+        const unsigned int t = __ldg(tab + c);
+        const float4* __restrict__ q = F + (t & 0xFFFFFFu);
+        if (COUNT) prim_tests += (res == 0.0f) ? 1u : 0u;
+        bool in, near;
+        float rho, margin;
+        switch (t >> 24) {
+            case OP_CYL: prim_cyl(q, x, y, z, in, near, rho); break;
+            case OP_SPHERE: prim_sphere(q, x, y, z, in, near, rho); break;
+            case OP_BOX: prim_box(q, x, y, z, in, near, rho); break;
+            case OP_PPED: prim_pped(q, x, y, z, in, near, rho); break;
+            default: prim_gyroid(q, x, y, z, in, near, rho, margin); break;
+        }
+        emit_child(in, near, rho, greedy, res, acc, unc, nhit);
+    }
+    float val = __saturatef(acc);
+    if (nhit >= 2 && fabsf(acc) < 1e-5f && res == 0.0f) unc = true;
+    if (res > 0.0f) val = res;
+    return val;
+}
+
+template <int SHAPE, int INTEG, bool COUNT, bool LIST>
 __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
                                                                        int i_coll, int i_tess) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles] [queue kQueueCap x nt ints]
     const Instr* sI = reinterpret_cast<const Instr*>(smem);
-    const float4* sF = reinterpret_cast<const float4*>(smem + (size_t)P.scene.n_instr * sizeof(Instr));
+    // LIST scenes (big collections) keep the fp32 pool in global memory: it would crowd out occupancy
+    const float4* sF = LIST ? P.scene.f32 : reinterpret_cast<const float4*>(smem + (size_t)P.scene.n_instr * sizeof(Instr));
     FastArgs* sA = reinterpret_cast<FastArgs*>(smem + P.smem_prog_bytes);
     double* sRay = reinterpret_cast<double*>(sA + 1);
     int* queue = reinterpret_cast<int*>(sRay + 6 * kBlockThreads);
@@ -176,7 +235,8 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
         const int nI = P.scene.n_instr * 2;
         for (int k = tid; k < nI; k += kBlockThreads) dst[k] = srcI[k];
         const uint4* srcF = reinterpret_cast<const uint4*>(P.scene.f32);
-        for (int k = tid; k < P.scene.f32_count; k += kBlockThreads) dst[nI + k] = srcF[k];
+        if (!LIST)
+            for (int k = tid; k < P.scene.f32_count; k += kBlockThreads) dst[nI + k] = srcF[k];
         if (tid == 0) {
             SceneView g;
             g.instr = P.scene.instr;
@@ -226,9 +286,15 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
     const int rb = is_coll ? i_coll + 1 : i_coll;
     const int re = is_coll ? (int)cw1.z : i_coll + 1;  // skip_to = matching COLL_END
     const unsigned int cflags = is_coll ? (cw0.z | 0x100u) : 0u;
-    const bool has_grid = is_coll && (cw0.z & F_HAS_GRID);
+    const bool has_grid = LIST || (is_coll && (cw0.z & F_HAS_GRID));
     const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
     const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
+    // cell-list grid sub-arrays (LIST): offsets are in the 5th record word, relative to `grids`
+    const uint4 lb = LIST ? *reinterpret_cast<const uint4*>(gF + 4) : make_uint4(0u, 0u, 0u, 0u);
+    const unsigned int* __restrict__ l_off = reinterpret_cast<const unsigned int*>(grids + lb.x);
+    const unsigned char* __restrict__ l_dist = reinterpret_cast<const unsigned char*>(grids + lb.y);
+    const unsigned short* __restrict__ l_idx = reinterpret_cast<const unsigned short*>(grids + lb.z);
+    const unsigned int* __restrict__ l_tab = reinterpret_cast<const unsigned int*>(grids + lb.w);
     const float4* tF = sF + (SHAPE == SHAPE_TESS ? reinterpret_cast<const uint4*>(sI + i_tess)[1].x : 0u);
     const int n_deform = P.scene.n_deform;
     const DeformRec* __restrict__ deform = P.scene.deform;
@@ -296,6 +362,7 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
         // clearance of this lane, in lattice steps, inside which density() is provably 0 (skipping):
         // 0 unless the lane sits in an empty grid cell / outside the tessellation's outer box
         float clear = 0.0f;
+        unsigned int lp = 0u, le = 0u;  // LIST: this lane's child list
         float tess_limit = 3.0e38f;  // object-space distance to the nearest unit-cell face / outer-box exit
         if (SHAPE == SHAPE_TESS) {
             const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
@@ -316,14 +383,25 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
                 const int ix = min(gx - 1, (int)(rx * gf.x));
                 const int iy = min(gy - 1, (int)(ry * gf.y));
                 const int iz = min(gz - 1, (int)(rz * gf.z));
-                uint2 mk = make_uint2(0u, 0u);
-                if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
-                if (mk.y >> 31) {  // empty cell: low byte = Chebyshev distance (cells) to the nearest occupied cell
-                    clear = (float)((mk.x & 255u) - 1u) * (gF[0].w * P.skip_m2s);
-                    mk = make_uint2(0u, 0u);
+                const unsigned int cell = (unsigned int)((iz * gy + iy) * gx + ix);
+                if (LIST) {
+                    if (alive) {
+                        lp = __ldg(l_off + cell);
+                        le = __ldg(l_off + cell + 1);
+                        if (lp == le) clear = (float)((unsigned int)__ldg(l_dist + cell) - 1u) * (gF[0].w * P.skip_m2s);
+                    }
+                    um_lo = __any_sync(FULL_MASK, lp < le) ? 1u : 0u;
+                    um_hi = 0u;
+                } else {
+                    uint2 mk = make_uint2(0u, 0u);
+                    if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + cell);
+                    if (mk.y >> 31) {  // empty cell: low byte = Chebyshev distance (cells) to the nearest occupied cell
+                        clear = (float)((mk.x & 255u) - 1u) * (gF[0].w * P.skip_m2s);
+                        mk = make_uint2(0u, 0u);
+                    }
+                    um_lo = __reduce_or_sync(FULL_MASK, mk.x);
+                    um_hi = __reduce_or_sync(FULL_MASK, mk.y);
                 }
-                um_lo = __reduce_or_sync(FULL_MASK, mk.x);
-                um_hi = __reduce_or_sync(FULL_MASK, mk.y);
             }
             // outside the outer box (Chebyshev distance m > 0) nothing can be hit for m / (ds * lip) steps
             if (act && !inside) clear = fmaxf(m - 4.0f * oc.w, 0.0f) * P.skip_m2s;
@@ -337,19 +415,33 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
             const int ix = min(gx - 1, max(0, __float2int_rd((x - g0.x) * g1.x)));
             const int iy = min(gy - 1, max(0, __float2int_rd((y - g0.y) * g1.y)));
             const int iz = min(gz - 1, max(0, __float2int_rd((z - g0.z) * g1.z)));
-            uint2 mk = make_uint2(0u, 0u);
-            if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + (unsigned int)((iz * gy + iy) * gx + ix));
-            if (mk.y >> 31) {
-                clear = (float)((mk.x & 255u) - 1u) * (g0.w * P.skip_m2s);
-                mk = make_uint2(0u, 0u);
+            const unsigned int cell = (unsigned int)((iz * gy + iy) * gx + ix);
+            if (LIST) {
+                if (alive) {
+                    lp = __ldg(l_off + cell);
+                    le = __ldg(l_off + cell + 1);
+                    if (lp == le) clear = (float)((unsigned int)__ldg(l_dist + cell) - 1u) * (g0.w * P.skip_m2s);
+                }
+                um_lo = __any_sync(FULL_MASK, lp < le) ? 1u : 0u;
+                um_hi = 0u;
+            } else {
+                uint2 mk = make_uint2(0u, 0u);
+                if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + cell);
+                if (mk.y >> 31) {
+                    clear = (float)((mk.x & 255u) - 1u) * (g0.w * P.skip_m2s);
+                    mk = make_uint2(0u, 0u);
+                }
+                um_lo = __reduce_or_sync(FULL_MASK, mk.x);
+                um_hi = __reduce_or_sync(FULL_MASK, mk.y);
             }
-            um_lo = __reduce_or_sync(FULL_MASK, mk.x);
-            um_hi = __reduce_or_sync(FULL_MASK, mk.y);
         }
         float rho = 0.0f;
         float clr = 3.0e38f;
         const bool evaluated = (um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive);
-        if (evaluated) rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
+        if (evaluated) {
+            if (LIST) rho = eval_list<COUNT>(sF, l_tab, l_idx, lp, le, cflags, x, y, z, alive, unc, prim_tests);
+            else rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
+        }
         if (evaluated && !has_grid && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
         rho *= dmf;
         unc = unc && act;
@@ -421,10 +513,10 @@ size_t fast_kernel_smem_bytes(const RenderParams& P) {
     return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double) + (size_t)kQueueCap * kBlockThreads * sizeof(int);
 }
 
-template <int SHAPE, int INTEG, bool COUNT>
+template <int SHAPE, int INTEG, bool COUNT, bool LIST>
 static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine, int i_coll, int i_tess, size_t smem, unsigned int grid,
                               cudaStream_t stream) {
-    auto kern = render_fast_kernel<SHAPE, INTEG, COUNT>;
+    auto kern = render_fast_kernel<SHAPE, INTEG, COUNT, LIST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kBlockThreads, smem, stream>>>(P, nfine, i_coll, i_tess);
@@ -433,20 +525,27 @@ static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine,
 
 // shape: SHAPE_FLAT / SHAPE_TESS; i_coll: index of the COLL_BEGIN (or of the lone primitive run);
 // i_tess: index of the TESS_BEGIN.
-cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, const unsigned char* d_nfine,
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, const unsigned char* d_nfine,
                                int i_coll, int i_tess, cudaStream_t stream) {
     const size_t smem = fast_kernel_smem_bytes(P);
     const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
     if (grid == 0) return cudaSuccess;
-#define XR_GO(S, I, C) return launch_one<S, I, C>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
+#define XR_GO(S, I, C, L) return launch_one<S, I, C, L>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
+#define XR_PICK(S, I)                                      \
+    do {                                                   \
+        if (count) { if (list) XR_GO(S, I, true, true); else XR_GO(S, I, true, false); } \
+        else { if (list) XR_GO(S, I, false, true); else XR_GO(S, I, false, false); }     \
+    } while (0)
     if (shape == SHAPE_FLAT) {
-        if (integrator == 0) { if (count) XR_GO(SHAPE_FLAT, 0, true); else XR_GO(SHAPE_FLAT, 0, false); }
-        else { if (count) XR_GO(SHAPE_FLAT, 1, true); else XR_GO(SHAPE_FLAT, 1, false); }
+        if (integrator == 0) XR_PICK(SHAPE_FLAT, 0);
+        else XR_PICK(SHAPE_FLAT, 1);
     } else {
-        if (integrator == 0) { if (count) XR_GO(SHAPE_TESS, 0, true); else XR_GO(SHAPE_TESS, 0, false); }
-        else { if (count) XR_GO(SHAPE_TESS, 1, true); else XR_GO(SHAPE_TESS, 1, false); }
+        if (integrator == 0) XR_PICK(SHAPE_TESS, 0);
+        else XR_PICK(SHAPE_TESS, 1);
     }
+#undef XR_PICK
 #undef XR_GO
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace xr

@@ -1047,6 +1047,152 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
     return true;
 }
 
+// Cell-list grid for big collections of primitives (> 63 children, so no 64-bit mask): per cell the
+// ascending list of children that may be non-zero there.  The kernel merges the lists of a warp's lanes
+// with a min-reduction, which visits the union in child order (greedy / summation order preserved).
+static bool build_list_grid(Builder& B, const Node& coll, const Box3* region, const std::vector<uint32_t>& child_f32,
+                            const std::vector<uint32_t>& child_f64, const std::vector<uint32_t>& child_op, uint32_t& f32_idx,
+                            uint32_t& grid_idx) {
+    const size_t n = coll.kids.size();
+    if (n > 65000) return false;
+    Box3 reg;
+    double feat = kInf;
+    std::vector<Box3> ext(n);
+    for (size_t c = 0; c < n; ++c) {
+        const Node& k = coll.kids[c];
+        ext[c] = node_extent(k);
+        if (ext[c].empty) continue;
+        for (int a = 0; a < 3; ++a)
+            if (!std::isfinite(ext[c].lo[a]) || !std::isfinite(ext[c].hi[a])) return false;  // unbounded child (gyroid)
+        if (!region) box_union(reg, ext[c]);
+        switch (k.type) {
+            case N_SPHERE: feat = std::fmin(feat, std::fabs(k.p[3])); break;
+            case N_CYL: feat = std::fmin(feat, std::fabs(k.p[6])); break;
+            case N_BOX: feat = std::fmin(feat, 0.5 * std::fmin(std::fabs(k.p[3]), std::fmin(std::fabs(k.p[4]), std::fabs(k.p[5])))); break;
+            case N_PPED: feat = std::fmin(feat, 0.5 * std::fmin(len3(k.p + 3), std::fmin(len3(k.p + 6), len3(k.p + 9)))); break;
+            default: break;
+        }
+    }
+    if (region) reg = *region;
+    if (reg.empty || !std::isfinite(feat)) return false;
+    double e3[3], emax = 0;
+    for (int a = 0; a < 3; ++a) {
+        e3[a] = reg.hi[a] - reg.lo[a];
+        if (!(e3[a] > 0) || !std::isfinite(e3[a])) return false;
+        emax = std::fmax(emax, e3[a]);
+    }
+    if (!(feat > 0)) feat = emax / 8;
+    const double cell = std::fmax(feat * g_grid_feat_scale, emax / g_grid_max);
+    int g[3];
+    for (int a = 0; a < 3; ++a) g[a] = std::max(1, std::min(g_grid_max, (int)std::ceil(e3[a] / cell)));
+    const size_t ncell = (size_t)g[0] * g[1] * g[2];
+    if (ncell <= 1) return false;
+    const double cs[3] = {e3[0] / g[0], e3[1] / g[1], e3[2] / g[2]};
+    const double margin = 1e-5 + 8.0 * B.ep;
+    std::vector<std::vector<uint16_t>> lists(ncell);
+    for (size_t c = 0; c < n; ++c) {
+        if (ext[c].empty) continue;
+        int lo_i[3], hi_i[3];
+        for (int a = 0; a < 3; ++a) {
+            lo_i[a] = std::max(0, std::min(g[a] - 1, (int)std::floor((ext[c].lo[a] - margin - reg.lo[a]) / cs[a])));
+            hi_i[a] = std::max(0, std::min(g[a] - 1, (int)std::floor((ext[c].hi[a] + margin - reg.lo[a]) / cs[a])));
+            // children hanging out of the region still have to be listed in the border cells (positions are clamped)
+        }
+        for (int iz = lo_i[2]; iz <= hi_i[2]; ++iz)
+            for (int iy = lo_i[1]; iy <= hi_i[1]; ++iy)
+                for (int ix = lo_i[0]; ix <= hi_i[0]; ++ix) {
+                    double lo[3] = {reg.lo[0] + ix * cs[0] - margin, reg.lo[1] + iy * cs[1] - margin, reg.lo[2] + iz * cs[2] - margin};
+                    double hi[3] = {reg.lo[0] + (ix + 1) * cs[0] + margin, reg.lo[1] + (iy + 1) * cs[1] + margin,
+                                    reg.lo[2] + (iz + 1) * cs[2] + margin};
+                    // border cells also stand in for everything beyond them (clamped lookups)
+                    if (ix == 0) lo[0] = -kInf;
+                    if (iy == 0) lo[1] = -kInf;
+                    if (iz == 0) lo[2] = -kInf;
+                    if (ix == g[0] - 1) hi[0] = kInf;
+                    if (iy == g[1] - 1) hi[1] = kInf;
+                    if (iz == g[2] - 1) hi[2] = kInf;
+                    bool touch;
+                    if (coll.kids[c].type == N_CYL && std::isfinite(lo[0] + lo[1] + lo[2] + hi[0] + hi[1] + hi[2]))
+                        touch = child_touches_cell(coll.kids[c], lo, hi);
+                    else if (coll.kids[c].type == N_SPHERE)
+                        touch = child_touches_cell(coll.kids[c], lo, hi);
+                    else {
+                        touch = true;
+                        for (int a = 0; a < 3; ++a)
+                            if (ext[c].hi[a] < lo[a] || ext[c].lo[a] > hi[a]) touch = false;
+                    }
+                    if (touch) lists[((size_t)iz * g[1] + iy) * g[0] + ix].push_back((uint16_t)c);
+                }
+    }
+    // Chebyshev distance (cells) from each empty cell to the nearest non-empty one
+    std::vector<int> dist(ncell, -1);
+    std::vector<size_t> frontier, next;
+    for (size_t c = 0; c < ncell; ++c)
+        if (!lists[c].empty()) {
+            dist[c] = 0;
+            frontier.push_back(c);
+        }
+    const bool periodic = region != nullptr;
+    int dd = 0;
+    while (!frontier.empty()) {
+        ++dd;
+        next.clear();
+        for (size_t c : frontier) {
+            const int ix = (int)(c % g[0]), iy = (int)((c / g[0]) % g[1]), iz = (int)(c / ((size_t)g[0] * g[1]));
+            for (int dz = -1; dz <= 1; ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        int jx = ix + dx, jy = iy + dy, jz = iz + dz;
+                        if (periodic) {
+                            jx = (jx + g[0]) % g[0];
+                            jy = (jy + g[1]) % g[1];
+                            jz = (jz + g[2]) % g[2];
+                        } else if (jx < 0 || jy < 0 || jz < 0 || jx >= g[0] || jy >= g[1] || jz >= g[2]) {
+                            continue;
+                        }
+                        const size_t q = ((size_t)jz * g[1] + jy) * g[0] + jx;
+                        if (dist[q] < 0) {
+                            dist[q] = dd;
+                            next.push_back(q);
+                        }
+                    }
+        }
+        frontier.swap(next);
+    }
+    // pack: cell_off (u32), cell_dist (u8), idx (u16), child_tab (u32) into the u64 pool
+    std::vector<uint32_t> off(ncell + 1, 0);
+    size_t total = 0;
+    for (size_t c = 0; c < ncell; ++c) {
+        off[c] = (uint32_t)total;
+        total += lists[c].size();
+    }
+    off[ncell] = (uint32_t)total;
+    grid_idx = (uint32_t)B.grids.size();
+    auto words = [](size_t bytes) { return (bytes + 7) / 8; };
+    const size_t w_off = words((ncell + 1) * 4), w_dist = words(ncell), w_idx = words(std::max<size_t>(1, total) * 2), w_tab = words(n * 4);
+    const size_t base_off = 0, base_dist = w_off, base_idx = w_off + w_dist, base_tab = w_off + w_dist + w_idx, base_tab64 = base_tab + w_tab;
+    B.grids.resize(B.grids.size() + w_off + w_dist + w_idx + 2 * w_tab, 0);
+    uint8_t* raw = reinterpret_cast<uint8_t*>(B.grids.data() + grid_idx);
+    memcpy(raw + base_off * 8, off.data(), (ncell + 1) * 4);
+    for (size_t c = 0; c < ncell; ++c) raw[base_dist * 8 + c] = (uint8_t)(dist[c] < 0 ? 255 : std::min(dist[c], 255));
+    uint16_t* idx = reinterpret_cast<uint16_t*>(raw + base_idx * 8);
+    size_t w = 0;
+    for (size_t c = 0; c < ncell; ++c)
+        for (uint16_t v : lists[c]) idx[w++] = v;
+    uint32_t* tab = reinterpret_cast<uint32_t*>(raw + base_tab * 8);
+    for (size_t c = 0; c < n; ++c) tab[c] = (child_op[c] << 24) | (child_f32[c] & 0xFFFFFFu);
+    uint32_t* tab64 = reinterpret_cast<uint32_t*>(raw + base_tab64 * 8);
+    for (size_t c = 0; c < n; ++c) tab64[c] = child_f64[c];
+    f32_idx = B.f32_idx();
+    B.f4(reg.lo[0], reg.lo[1], reg.lo[2], std::fmin(cs[0], std::fmin(cs[1], cs[2])));
+    B.f4(1.0 / cs[0], 1.0 / cs[1], 1.0 / cs[2], 0);
+    B.f4bits((uint32_t)g[0], (uint32_t)g[1], (uint32_t)g[2], 0);
+    B.f4(g[0], g[1], g[2], 0);
+    B.f4bits((uint32_t)base_off, (uint32_t)base_dist, (uint32_t)base_idx, (uint32_t)base_tab);
+    B.f4bits((uint32_t)base_tab64, 0, 0, 0);
+    return true;
+}
+
 static bool emit_node(Builder& B, const Node& n, bool nosave, uint32_t child_bit);
 
 static bool emit_collection(Builder& B, const Node& coll, bool nosave, uint32_t child_bit, const Box3* region) {
@@ -1071,6 +1217,8 @@ static bool emit_collection(Builder& B, const Node& coll, bool nosave, uint32_t 
         B.save_depth_max = std::max(B.save_depth_max, B.save_depth);
     }
     size_t i = 0, nk = coll.kids.size();
+    std::vector<uint32_t> child_f32(nk, 0), child_f64(nk, 0), child_op(nk, 0);
+    bool all_prims = true;
     while (i < nk) {
         const Node& k = coll.kids[i];
         if (is_prim(k.type)) {
@@ -1081,6 +1229,9 @@ static bool emit_collection(Builder& B, const Node& coll, bool nosave, uint32_t 
             ir.f32_idx = B.f32_idx();
             ir.f64_idx = B.f64_idx();
             while (j < nk && coll.kids[j].type == k.type && (j - i) < 64 && (j / 64 == i / 64)) {
+                child_f32[j] = B.f32_idx();
+                child_f64[j] = B.f64_idx();
+                child_op[j] = (uint32_t)ir.op;
                 emit_prim_params(B, coll.kids[j]);
                 ++j;
             }
@@ -1088,8 +1239,17 @@ static bool emit_collection(Builder& B, const Node& coll, bool nosave, uint32_t 
             B.instr.push_back(ir);
             i = j;
         } else {
+            all_prims = false;
             if (!emit_node(B, k, false, (uint32_t)i)) return false;
             ++i;
+        }
+    }
+    if (!(B.instr[begin].flags & F_HAS_GRID) && all_prims && nk > 63) {
+        uint32_t lf = 0, li = 0;
+        if (build_list_grid(B, coll, region, child_f32, child_f64, child_op, lf, li)) {
+            B.instr[begin].flags |= F_HAS_LIST;
+            B.instr[begin].f32_idx = lf;
+            B.instr[begin].aux = li;
         }
     }
     Instr ie = {};
