@@ -262,3 +262,17 @@ def test_skipping_changes_nothing(X, scenes):
         assert np.abs(a.astype(np.float64) - b).max() <= 2e-6
         assert sa["ref_samples"] == sb["ref_samples"]
         assert sa["evaluated_samples"] < sb["evaluated_samples"]
+
+
+def test_degenerate_cameras_are_refused(X, scenes):
+    """polar = 0 makes LookAtV singular (main.go:236-237): the camera matrix is all zero (mgl64 Inv of a singular
+    matrix) or NaN.  The reference would write garbage images; the plugin returns error 2 instead of marching."""
+    sc = X.Scene(str(scenes / "cube_w_hole.json"))
+    cam = X.camera_from_angles(30.0, 0.0, 4.0, 40.0)
+    cams = (X._lib.XRayCameraParams64 * 1)(cam)
+    with pytest.raises(X._lib.XRayError, match="degenerate"):
+        X.render_scene(sc, cams, 8)
+    good = X.camera_from_angles(30.0, 90.0, 4.0, 40.0)
+    good.fov_y = 190.0
+    with pytest.raises(X._lib.XRayError, match="degenerate"):
+        X.render_scene(sc, (X._lib.XRayCameraParams64 * 1)(good), 8)

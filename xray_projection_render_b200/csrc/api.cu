@@ -636,6 +636,16 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
     const Header* h = (const Header*)scene->blob.data();
     for (int s = 0; s < (int)h->n_voxel_slots; ++s)
         if (!scene->vox[s].data && !(s == 0 && borrowed_vox)) return fail(2, "voxel_grid slot has no data (XRaySceneSetVoxelData)");
+    // Degenerate cameras (polar = 0 or 180 deg makes LookAtV singular -> NaN matrix, main.go:236-237) would turn
+    // into NaN rays; the reference then writes NaN images.  Refuse them instead of marching garbage.
+    for (int v = 0; v < n; ++v) {
+        bool ok = std::isfinite(cams[v].R) && std::isfinite(cams[v].fov_y) && cams[v].fov_y > 0.0 && cams[v].fov_y < 180.0;
+        for (int a = 0; a < 3 && ok; ++a) ok = std::isfinite(cams[v].eye[a]);
+        for (int a = 0; a < 16 && ok; ++a) ok = std::isfinite(cams[v].view[a]);
+        if (ok && !(std::fabs(cams[v].view[15]) > 1e-12)) ok = false;  // TransformCoordinate divides by w
+        if (!ok) return fail(2, "camera " + std::to_string(v) + " is degenerate (non-finite matrix, fov outside (0,180) or w = 0)");
+    }
+    if (!std::isfinite(opts.flat_field) || !std::isfinite(opts.density_multiplier)) return fail(2, "flat_field / density_multiplier must be finite");
     double ds;
     if (int rc = resolve_ds(scene, opts.ds, ds)) return rc;
 
