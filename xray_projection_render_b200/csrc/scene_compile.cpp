@@ -937,9 +937,9 @@ static bool child_touches_cell(const Node& k, const double* lo, const double* hi
     }
 }
 
-static int g_grid_max = 32;  // cells per axis cap (env XRAY_GRID_MAX)
+static int g_grid_max = 32;  // the grid holds at most g_grid_max^3 cells, at most 4*g_grid_max per axis (env XRAY_GRID_MAX)
 static int g_grid_min_children = 4;
-static double g_grid_feat_scale = 0.5;  // cell size in units of the smallest child feature (env XRAY_GRID_FEAT_SCALE)
+static double g_grid_feat_scale = 0.25;  // cell size in units of the smallest child feature (env XRAY_GRID_FEAT_SCALE)
 
 // Child-mask grid for a collection: cell -> 64-bit set of children that may be non-zero there.
 // region: where the collection is evaluated (unit-cell bounds) or null (use children extents).
@@ -973,9 +973,11 @@ static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_
         }
     if (!std::isfinite(feat)) return false;  // no bounded child: every cell would list every child
     if (!(feat > 0)) feat = emax / 8;
-    double cell = std::fmax(feat * g_grid_feat_scale, emax / g_grid_max);
+    // cubic cells: as fine as the smallest feature asks for, within a budget of g_grid_max^3 cells
+    double cell = std::fmax(std::fmax(feat * g_grid_feat_scale, emax / (4.0 * g_grid_max)),
+                            std::cbrt(ext[0] * ext[1] * ext[2] / ((double)g_grid_max * g_grid_max * g_grid_max)));
     int g[3];
-    for (int i = 0; i < 3; ++i) g[i] = std::max(1, std::min(g_grid_max, (int)std::ceil(ext[i] / cell)));
+    for (int i = 0; i < 3; ++i) g[i] = std::max(1, std::min(4 * g_grid_max, (int)std::ceil(ext[i] / cell - 1e-9)));
     if (g[0] * g[1] * g[2] <= 1) return false;
     double margin = 1e-5 + 8.0 * B.ep;
     grid_idx = (uint32_t)B.grids.size();
@@ -1082,9 +1084,10 @@ static bool build_list_grid(Builder& B, const Node& coll, const Box3* region, co
         emax = std::fmax(emax, e3[a]);
     }
     if (!(feat > 0)) feat = emax / 8;
-    const double cell = std::fmax(feat * g_grid_feat_scale, emax / g_grid_max);
+    const double cell = std::fmax(std::fmax(feat * g_grid_feat_scale, emax / (4.0 * g_grid_max)),
+                                  std::cbrt(e3[0] * e3[1] * e3[2] / ((double)g_grid_max * g_grid_max * g_grid_max)));
     int g[3];
-    for (int a = 0; a < 3; ++a) g[a] = std::max(1, std::min(g_grid_max, (int)std::ceil(e3[a] / cell)));
+    for (int a = 0; a < 3; ++a) g[a] = std::max(1, std::min(4 * g_grid_max, (int)std::ceil(e3[a] / cell - 1e-9)));
     const size_t ncell = (size_t)g[0] * g[1] * g[2];
     if (ncell <= 1) return false;
     const double cs[3] = {e3[0] / g[0], e3[1] / g[1], e3[2] / g[2]};
