@@ -218,36 +218,53 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
         }
     }
 
-    // (2) interior samples, cell-synchronous
+    // (2) interior samples, cell-synchronous.
+    // Cell index by magic-number rounding on the FMA pipe instead of FRND/F2I on the (4x slower) XU pipe:
+    // r = (u - 0.5) + 1.5*2^23 rounds u - 0.5 to the nearest integer.  Where that differs from floor(u)
+    // (u an exact integer, ties-to-even) the weight comes out as exactly 1 or 0 on the neighbouring cell,
+    // which is the same value because the interpolant is continuous across cell faces.
+    const float kMagic = 12582912.0f;  // 1.5 * 2^23, bit pattern 0x4B400000 (ulp = 1 there)
+    // work with v = u - 0.5 so that v + kMagic rounds to floor(u) (nearest integer of u - 0.5)
+    const float vcx = ucx - 0.5f, vcy = ucy - 0.5f, vcz = ucz - 0.5f;
+    // Per-cell run length by DDA: the lattice is uniform to ~1e-12, so inside a cell the weights advance
+    // by dw = du*ds per sample and the number of samples before the ray leaves the cell is
+    // ceil(min_i dist_i/|dw_i|), dist_i = distance to the exit face = 0.5 - (w_i - 0.5)*sign(dw_i).
+    // A face sample charged to the "wrong" side is evaluated 1e-6 outside its cell: same value to 1e-6.
+    const float dwx = dux * P.ds_f, dwy = duy * P.ds_f, dwz = duz * P.ds_f;
+    const float ivx = fabsf(dwx) > 1e-12f ? 1.0f / dwx : 0.0f, hvx = fabsf(dwx) > 1e-12f ? 0.5f / fabsf(dwx) : 1e30f;
+    const float ivy = fabsf(dwy) > 1e-12f ? 1.0f / dwy : 0.0f, hvy = fabsf(dwy) > 1e-12f ? 0.5f / fabsf(dwy) : 1e30f;
+    const float ivz = fabsf(dwz) > 1e-12f ? 1.0f / dwz : 0.0f, hvz = fabsf(dwz) > 1e-12f ? 0.5f / fabsf(dwz) : 1e30f;
     float acc = 0.0f, cmp = 0.0f;  // Kahan over per-cell partial sums
     int k = m0;
     const int kend = hit ? m1 : m0;
     const float* __restrict__ ttab = P.t_tab;
     while (__any_sync(FULL_MASK, k < kend)) {
         const bool live = k < kend;
-        float t = ttab[live ? k : 0];
-        float ux = fmaf(dux, t, ucx), uy = fmaf(duy, t, ucy), uz = fmaf(duz, t, ucz);
-        const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
-        const int z0 = max(0, min(nz - 1, (int)fz));
+        const float t = ttab[live ? k : 0];
+        const float vx = fmaf(dux, t, vcx), vy = fmaf(duy, t, vcy), vz = fmaf(duz, t, vcz);
+        const float rx = vx + kMagic, ry = vy + kMagic, rz = vz + kMagic;  // cell id (as magic floats)
+        const float fx = rx - kMagic, fy = ry - kMagic, fz = rz - kMagic;  // cell origin (integers)
+        float wx = vx - (fx - 0.5f), wy = vy - (fy - 0.5f), wz = vz - (fz - 0.5f);  // = u - f in [0, 1]
+        const int z0 = max(0, min(nz - 1, __float_as_int(rz) - 0x4B400000));
         const int z1 = min(z0 + 1, nz - 1);
         const float4 a = gather_layer(tex, z0, fy + 1.0f, fx + 1.0f);
         const float4 b = gather_layer(tex, z1, fy + 1.0f, fx + 1.0f);
         if (live) {
+            const float steps = fminf(fmaf(0.5f - wx, ivx, hvx), fminf(fmaf(0.5f - wy, ivy, hvy), fmaf(0.5f - wz, ivz, hvz)));
+            const int n = max(1, min(kend - k, __float2int_ru(fminf(steps, 1.0e6f))));
+            // z-lerp differences once per cell
+            const float d00 = b.w - a.w, d01 = b.z - a.z, d10 = b.x - a.x, d11 = b.y - a.y;
             float part = 0.0f;
-            for (;;) {
-                const float wx = ux - fx, wy = uy - fy, wz = uz - fz;
-                const float v00 = fmaf(wz, b.w - a.w, a.w), v01 = fmaf(wz, b.z - a.z, a.z);  // x0: y0, y1
-                const float v10 = fmaf(wz, b.x - a.x, a.x), v11 = fmaf(wz, b.y - a.y, a.y);  // x1: y0, y1
+            for (int q = 0; q < n; ++q) {
+                const float v00 = fmaf(wz, d00, a.w), v01 = fmaf(wz, d01, a.z);  // x0: y0, y1
+                const float v10 = fmaf(wz, d10, a.x), v11 = fmaf(wz, d11, a.y);  // x1: y0, y1
                 const float v0 = fmaf(wy, v01 - v00, v00), v1 = fmaf(wy, v11 - v10, v10);
                 part += fmaf(wx, v1 - v0, v0);
-                ++k;
-                if (k >= kend) break;
-                t = ttab[k];
-                ux = fmaf(dux, t, ucx);
-                uy = fmaf(duy, t, ucy);
-                uz = fmaf(duz, t, ucz);
-                if (floorf(ux) != fx || floorf(uy) != fy || floorf(uz) != fz) break;
+                wx += dwx;
+                wy += dwy;
+                wz += dwz;
             }
+            k += n;
             const float y_ = part - cmp;
             const float t_ = acc + y_;
             cmp = (t_ - acc) - y_;
