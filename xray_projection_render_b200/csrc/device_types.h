@@ -54,6 +54,7 @@ struct RenderParams {
     unsigned long long* stats;  // device, XRAY_NUM_STATS counters or null
     float dm_f, ds_f, ds_fine_f;  // fp32 copies for the hot loop (no F2F per iteration)
     float skip_m2s;             // object-space clearance -> number of lattice steps that stay inside it (0 disables skipping)
+    int dbg_cause;              // COUNT variants only: count fp64 fallbacks of this cause mask (0 = all)
 };
 
 constexpr int kBlockThreads = 128;

@@ -23,10 +23,20 @@ struct FastArgs {  // uniform per-launch scalars the hot loop needs, staged in s
     SceneView gsv;  // global-memory view of the program for the exact path
 };
 
+// Exact lattice position: coarse sample `base` (nsub = 0), or fine sample j of coarse interval `base`
+// (nsub = j + 1): s_tab[base] with ds_fine added nsub times, as main.go:181-186 does.
+__device__ __forceinline__ double exact_position(const double* __restrict__ s_tab, int base, int nsub, double ds_fine) {
+    double left = s_tab[base];
+    for (int q = 0; q < nsub; ++q) left = dadd(left, ds_fine);
+    return left;
+}
+
 // Cold path: exact fp64 density at lattice position s for the lanes in `need`.
 // Out of line on purpose: it must not dilute the hot loop's instruction footprint.
-__device__ __noinline__ float exact_density_cold(const SceneView* sv, const double* ray, double s, double dm, bool need) {
+__device__ __noinline__ float exact_density_cold(const SceneView* sv, const double* ray, const double* __restrict__ s_tab, int base,
+                                                 int nsub, double ds_fine, double dm, bool need) {
     const int tid = threadIdx.x;
+    const double s = exact_position(s_tab, base, nsub, ds_fine);
     // ray[] is [6][blockDim]: o.x o.y o.z d.x d.y d.z
     const double x = dadd(ray[0 * kBlockThreads + tid], dmul(ray[3 * kBlockThreads + tid], s));
     const double y = dadd(ray[1 * kBlockThreads + tid], dmul(ray[4 * kBlockThreads + tid], s));
@@ -40,12 +50,26 @@ __device__ __noinline__ float exact_density_cold(const SceneView* sv, const doub
     return rho;
 }
 
-// Exact position of fine sample j (0-based) of coarse interval kf: s_tab[kf] + ds_fine added (j+1) times.
-__device__ __noinline__ double fine_position_cold(const double* s_tab, int kf, int j, double ds_fine) {
-    double left = s_tab[kf];
-    for (int q = 0; q <= j; ++q) left = dadd(left, ds_fine);
-    return left;
+// Cold path for samples within the guard band of a tessellation's outer box or of a unit-cell face: only the
+// period (and the inclusive bounds tests of objects.go:569,459) is in doubt, not the primitives.  Redo position,
+// warp and fold in fp64 exactly as the reference does and hand the folded point back to the fp32 pipeline
+// (.w = 1 when the sample survives both bounds tests).  ~5x cheaper than a full exact evaluation, and it is
+// the whole cost of rays that run inside a cell-face plane (the central pixel row at polar = 90 deg).
+__device__ __noinline__ float4 exact_fold_cold(const SceneView* sv, const double* ray, const double* __restrict__ s_tab, int base,
+                                               int nsub, double ds_fine, int tess_f64_idx) {
+    const int tid = threadIdx.x;
+    const double s = exact_position(s_tab, base, nsub, ds_fine);
+    double x = dadd(ray[0 * kBlockThreads + tid], dmul(ray[3 * kBlockThreads + tid], s));
+    double y = dadd(ray[1 * kBlockThreads + tid], dmul(ray[4 * kBlockThreads + tid], s));
+    double z = dadd(ray[2 * kBlockThreads + tid], dmul(ray[5 * kBlockThreads + tid], s));
+    for (int i = 0; i < sv->n_deform; ++i) Exact::deform(sv->deform[i], x, y, z);
+    Instr I = {};
+    I.f64_idx = (unsigned int)tess_f64_idx;
+    bool dummy = false;
+    const bool ok = Exact::tess(*sv, I, x, y, z, dummy);
+    return make_float4((float)x, (float)y, (float)z, ok ? 1.0f : 0.0f);
 }
+
 
 enum Shape { SHAPE_FLAT = 1, SHAPE_TESS = 2 };
 
@@ -296,6 +320,7 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
     const unsigned short* __restrict__ l_idx = reinterpret_cast<const unsigned short*>(grids + lb.z);
     const unsigned int* __restrict__ l_tab = reinterpret_cast<const unsigned int*>(grids + lb.w);
     const float4* tF = sF + (SHAPE == SHAPE_TESS ? reinterpret_cast<const uint4*>(sI + i_tess)[1].x : 0u);
+    const int tess_f64_idx = SHAPE == SHAPE_TESS ? (int)reinterpret_cast<const uint4*>(sI + i_tess)[1].y : 0;
     const int n_deform = P.scene.n_deform;
     const DeformRec* __restrict__ deform = P.scene.deform;
 
@@ -369,14 +394,28 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
             const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
             const float qx = (x - um.x) * id.x, qy = (y - um.y) * id.y, qz = (z - um.z) * id.z;
             const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
-            const float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+            float rx = qx - fx, ry = qy - fy, rz = qz - fz;
             const float lo = fminf(rx, fminf(ry, rz)), hi = fmaxf(rx, fmaxf(ry, rz));
-            const bool inside = m <= 0.0f;  // outer bounds inclusive (objects.go:569)
-            unc = alive && ((fabsf(m) < oc.w) || (inside && (lo < id.w || hi > 1.0f - id.w)));
-            alive = alive && inside;
+            bool inside = m <= 0.0f;  // outer bounds inclusive (objects.go:569)
+            const bool edge = alive && ((fabsf(m) < oc.w) || (inside && (lo < id.w || hi > 1.0f - id.w)));
             x = fmaf(-dd.x, fx, x);
             y = fmaf(-dd.y, fy, y);
             z = fmaf(-dd.z, fz, z);
+            if (__any_sync(FULL_MASK, edge)) {  // period / bounds in doubt: exact fold, then carry on in fp32
+                const float4 e = exact_fold_cold(&sA->gsv, sRay, P.s_tab, mode == 0 ? k + (INTEG == 1 ? 1 : 0) : kf,
+                                                 mode == 0 ? 0 : jf + 1, P.ds_fine, tess_f64_idx);
+                if (edge) {
+                    x = e.x;
+                    y = e.y;
+                    z = e.z;
+                    inside = e.w != 0.0f;
+                    rx = (x - um.x) * id.x;
+                    ry = (y - um.y) * id.y;
+                    rz = (z - um.z) * id.z;
+                    if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & (fabsf(m) < oc.w ? 1 : 2)))) ++n_fallback;
+                }
+            }
+            alive = alive && inside;
             if (has_grid) {  // the grid spans exactly the unit cell: cell = floor(fraction * g), fraction in [0,1]
                 const float4 gd = gF[2], gf = gF[3];
                 const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
@@ -446,13 +485,11 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
         rho *= dmf;
         unc = unc && act;
         if (__any_sync(FULL_MASK, unc)) {
-            double s_exact;
-            if (mode == 0) s_exact = P.s_tab[k + (INTEG == 1 ? 1 : 0)];
-            else s_exact = fine_position_cold(P.s_tab, kf, jf, P.ds_fine);
-            const float r = exact_density_cold(&sA->gsv, sRay, s_exact, P.dm, unc);
+            const float r = exact_density_cold(&sA->gsv, sRay, P.s_tab, mode == 0 ? k + (INTEG == 1 ? 1 : 0) : kf,
+                                               mode == 0 ? 0 : jf + 1, P.ds_fine, P.dm, unc);
             if (unc) {
                 rho = r;
-                if (COUNT) ++n_fallback;
+                if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & 4))) ++n_fallback;
             }
         }
 

@@ -842,7 +842,10 @@ static void emit_prim_params(Builder& B, const Node& n) {
             double wmax = lv + r + 8 * ep;
             double tolc_raw = vv > 0 ? (1.7321 * ep * lv + 6.0 * u * wmax * lv) / vv + 4.0 * u : 1.0;
             double tolc = 2.0 * tolc_raw;
-            double tolr = 2.0 * (2.0 * r * (1.7321 * ep + lv * tolc_raw + 6.0 * u * wmax) + 6.0 * u * r * r + 3 * ep * ep);
+            // d^2 = |e|^2, e = w - v*c.  The exact e is orthogonal to v, so the error of c moves the computed e
+            // along the axis and enters d^2 only at second order; first order is 2*r*|dw| (position + rounding).
+            double e2 = 1.7321 * ep + lv * tolc_raw + 6.0 * u * wmax;
+            double tolr = 2.0 * (2.0 * r * (1.7321 * ep + 6.0 * u * wmax) + e2 * e2 + 6.0 * u * r * r);
             B.f4(p[0], p[1], p[2], p[7]);
             B.f4(v[0], v[1], v[2], inv_vv);
             B.f4(p[6] * p[6], up32(tolr), up32(tolc), up32(tolc) / up32(tolr));  // .w rescales the radial slack onto tolc
@@ -874,7 +877,9 @@ static void emit_prim_params(Builder& B, const Node& n) {
             double amax = (3.0 + cmax) / std::fabs(scale);  // |argument| bound inside the render window
             double argerr = ep / std::fabs(scale) + 3.0 * u * amax;
             // + 1e-6 per sin/cos: SFU evaluation after Cody-Waite reduction (eval.cuh fast_sincos)
-            double tol = 2.0 * (6.0 * (argerr + 1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
+            // argument errors: d(sin a cos b) <= da|cos a cos b| + db|sin a sin b| <= max(da,db) per term (3 terms);
+            // function errors: 6 SFU evaluations, each multiplied by a factor <= 1
+            double tol = 2.0 * (3.0 * argerr + 6.0 * (1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
             B.f4(p[0], p[1], p[2], p[5]);
             // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
             B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
