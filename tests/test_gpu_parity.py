@@ -276,3 +276,25 @@ def test_degenerate_cameras_are_refused(X, scenes):
     good.fov_y = 190.0
     with pytest.raises(X._lib.XRayError, match="degenerate"):
         X.render_scene(sc, (X._lib.XRayCameraParams64 * 1)(good), 8)
+
+
+@pytest.mark.parametrize("Rcam,fov,promoted", [(40.0, 40.0, True), (40.0, 4.0, False), (4.0, 120.0, False), (1.9, 60.0, False)])
+def test_far_wide_and_near_cameras(X, O, scenes, Rcam, fov, promoted):
+    """fp32 mode is only sound while |o + d*R| keeps the fp32 position error under the guard-band budget; a distant
+    camera must be rendered by the fp64 kernels instead (api.cu fp32_position_bound_ok).  Seen from outside: the
+    fp32-mode image then agrees with the oracle to float rounding and nothing is skipped.  Wide and near cameras
+    (eye inside the sample window) stay on the fp32 kernels and must hold the fp32 tolerance."""
+    obj = str(scenes / "lattice.json")
+    sc, osc = X.Scene(obj), O.OracleScene(obj)
+    ds, res = 0.02, (192 if promoted else 24)
+    views = [(100.0, 80.0)]
+    cams = X.cameras_from_angles(views, Rcam, fov)
+    ref, nref = oracle_images(O, osc, views, res, ds, "hierarchical", R=Rcam, fov=fov)
+    img, st = X.render_scene(sc, cams, res, precision="fp32", ds=ds, return_stats=True)
+    assert st["ref_samples"] == nref
+    if promoted:
+        assert np.abs(img.astype(np.float64) - ref).max() <= 1e-6
+        assert st["fp64_fallbacks"] == 0  # the exact kernel has no guard band
+    else:
+        assert np.abs(img.astype(np.float64) - ref).max() <= TOL_FP32
+        assert st["evaluated_samples"] < nref  # fp32 kernel: culled / skipped samples are not evaluated

@@ -619,6 +619,39 @@ static int resolve_ds(const XRayScene* sc, double ds_in, double& ds) {
     return 0;
 }
 
+// Largest |coordinate| of pc = o + d*R over the corner rays of every camera (the extremes of a pinhole fan),
+// rays built like eval.cuh make_ray (main.go:457-465).
+static bool fp32_position_bound_ok(const Header* h, const XRayCameraParams64* cams, int n, int res) {
+    const double kU32 = 5.9604644775390625e-08, tmax = 1.75;
+    double pcmax = 0.0;
+    for (int v = 0; v < n; ++v) {
+        const XRayCameraParams64& c = cams[v];
+        const double f = 1.0 / std::tan(c.fov_y * 3.14159265358979323846 / 360.0);
+        const double ext[2] = {-1.0, 1.0 - 2.0 / (double)res};
+        for (int q = 0; q < 4; ++q) {
+            const double px = ext[q & 1], py = ext[q >> 1], pz = -f;
+            double t[4];
+            for (int r = 0; r < 4; ++r) t[r] = c.view[r * 4 + 0] * px + c.view[r * 4 + 1] * py + c.view[r * 4 + 2] * pz + c.view[r * 4 + 3];
+            double dv[3], l = 0.0;
+            for (int a = 0; a < 3; ++a) {
+                dv[a] = t[a] / t[3] - c.eye[a];
+                l += dv[a] * dv[a];
+            }
+            l = std::sqrt(l);
+            if (!(l > 0.0)) return false;
+            for (int a = 0; a < 3; ++a) pcmax = std::fmax(pcmax, std::fabs(c.eye[a] + dv[a] / l * c.R));
+        }
+    }
+    if (!std::isfinite(pcmax)) return false;
+    double amax = 0.0;
+    for (int a = 0; a < 3; ++a) amax = std::fmax(amax, std::fmax(std::fabs(h->aabb_lo[a]), std::fabs(h->aabb_hi[a])));
+    const double xmax = std::fmin(pcmax + tmax, std::isfinite(amax) ? amax + 0.01 : 1e300);  // only positions inside the scene matter
+    const double base = 1.0e-6;  // kEpsPosBase (scene_compile.cpp): the budget for the un-warped position
+    if (kU32 * (2.0 * tmax + pcmax + xmax) * 1.25 > base) return false;
+    if (h->n_deform > 0 && pcmax + tmax > 4.0) return false;  // warp error terms assume |x| <= 4 (scene_compile.cpp deform_eps_pos)
+    return true;
+}
+
 static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n, int res, const XRayRenderOpts* opts_in,
                          void* out, bool out_on_device, const void* borrowed_vox, bool fast_volume) {
     if (!scene || !cams || !out) return fail(1, "null pointer argument");
@@ -649,6 +682,16 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
     if (!std::isfinite(opts.flat_field) || !std::isfinite(opts.density_multiplier)) return fail(2, "flat_field / density_multiplier must be finite");
     double ds;
     if (int rc = resolve_ds(scene, opts.ds, ds)) return rc;
+
+    // fp32 mode is only sound while every sample position x = fma(fl(d), fl(s - R), fl(o + d*R)) stays within
+    // the position error the guard bands were derived for (Header.eps_pos = 1e-6 x warp Lipschitz):
+    // |dx| <= u32 * (2*|t|max + |pc| + |x|).  A distant camera or a wide field of view puts pc = o + d*R far
+    // from the origin; such calls are promoted to the fp64 kernels (slower, always exact) instead of risking a
+    // misclassified sample.
+    if (opts.precision == XRAY_PRECISION_FP32 && !fp32_position_bound_ok(h, cams, n, res)) {
+        opts.precision = XRAY_PRECISION_FP64;
+        fast_volume = false;
+    }
 
     std::vector<int> devs;
     if (out_on_device || opts.num_devices <= 0) {
