@@ -195,3 +195,39 @@ def test_scene_voxeliser_matches_oracle(X, O, scenes):
         for k, i, j in rng.integers(0, res, size=(600, 3)):
             want = osc.density(i / res * 2.0 - 1.0, j / res * 2.0 - 1.0, k / res * 2.0 - 1.0)
             assert vol[k, i, j] == np.float32(want)
+
+
+def _render_ext_vs_oracle(X, O, vol, cams, res, ds, ff=0.03):
+    osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)}, flat_field=ff)
+    ref = np.stack([osc.render_view(np.array(list(c.eye)), np.array(list(c.view)).reshape(4, 4), res, float(c.fov_y),
+                                    float(c.R), ds, "simple")[0] for c in cams])
+    img = X.render_volume(vol, cams, res, integration="simple", precision="fp32", ds=ds, flat_field=ff)
+    return float(np.abs(img.astype(np.float64) - ref).max())
+
+
+@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5])
+def test_every_warp_footprint(X, O, monkeypatch, tile):
+    """The voxel kernel is instantiated for six warp pixel footprints (render_volume.cu); the launcher picks one from
+    the camera orientation.  Force each in turn: odd resolution (partial tiles, scalar stores), rough field."""
+    monkeypatch.setenv("XRAY_VOLUME_TILE", str(tile))
+    rng = np.random.default_rng(100 + tile)
+    vol = rng.random((20, 28, 24), dtype=np.float32)
+    cams = X.cameras_from_angles([(10.0, 90.0), (75.0, 65.0)], R, FOV)
+    assert _render_ext_vs_oracle(X, O, vol, cams, 27, 2.0 / 20 / 5.0) <= TOL_FP32
+
+
+def test_rolled_camera_and_long_cell_runs(X, O):
+    """A camera rolled by 90 deg about its axis swaps which image axis follows z (the launcher then lays the warp
+    along j), and a step of 1/60 voxel makes every cell hold ~60 samples: the closed-form per-cell sum
+    (sum of a cubic in the step index) must still match the per-sample reference loop."""
+    rng = np.random.default_rng(77)
+    vol = rng.random((16, 16, 16), dtype=np.float32)
+    cams = X.cameras_from_angles([(33.0, 90.0), (140.0, 70.0)], R, FOV)
+    for c in cams:
+        v = list(c.view)
+        for r in range(3):
+            v[r * 4 + 0], v[r * 4 + 1] = v[r * 4 + 1], -v[r * 4 + 0]
+        for k in range(16):
+            c.view[k] = v[k]
+    assert _render_ext_vs_oracle(X, O, vol, cams, 20, 2.0 / 16 / 60.0) <= TOL_FP32
+    assert _render_ext_vs_oracle(X, O, vol, cams, 20, 2.0 / 16 / 0.7) <= TOL_FP32  # steps longer than a voxel

@@ -33,6 +33,7 @@ cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator,
                                int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
+                                     int warp_shape,
                                      cudaStream_t stream);
 cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
                                       const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
@@ -249,6 +250,22 @@ struct Job {
     int rc;
     std::string err;
 };
+
+// Pixel footprint of a warp in the voxel kernel (render_volume.cu launch_render_volume_tex).  Texture layers are
+// z slices, so lanes should sit side by side along the image axis that moves least in z: camera x (matrix column 0)
+// for the usual CT geometry (polar = 90 deg), camera y when the camera is rolled; the square-ish 4 x 8 otherwise.
+static int volume_warp_shape(const Job& J, int v0, int n) {
+    if (const char* e = getenv("XRAY_VOLUME_TILE")) return atoi(e);
+    double zi = 0.0, zj = 0.0;
+    for (int v = v0; v < v0 + n; ++v) {
+        const XRayCameraParams64& c = J.cams[J.views[v]];
+        zi += std::fabs(c.view[2 * 4 + 0]);
+        zj += std::fabs(c.view[2 * 4 + 1]);
+    }
+    if (zi <= 0.5 * zj) return 1;  // 32 x 1 (i x j)
+    if (zj <= 0.5 * zi) return 2;  // 1 x 32
+    return 0;
+}
 
 // Persistent per-device scratch: grow-only buffers, cached sample-lattice tables, one stream.
 // Keeps the steady-state render path free of cudaMalloc/cudaFree (both synchronise the device).
@@ -516,7 +533,7 @@ static int run_job(Job& J) {
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
-                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, stream);
+                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, v0, n), stream);
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);

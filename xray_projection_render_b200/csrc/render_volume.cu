@@ -156,11 +156,25 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int laye
     return r;  // .w=(y0,x0) .z=(y1,x0) .x=(y0,x1) .y=(y1,x1)
 }
 
+// WI x WJ = the pixel footprint of one warp (i = camera x, j = camera y; j is the fast output index).  The best
+// shape is the one whose lanes share texture layers (z): the launcher picks it from the camera orientation.
+template <int WI, int WJ>
 __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const RenderParams P, cudaTextureObject_t tex,
                                                                          const float* __restrict__ vol, int nx, int ny, int nz,
                                                                          float tol) {
+    static_assert(WI * WJ == 32, "one warp");
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
+    {  // block = 2 x 2 warps
+        const int tj_n = (P.res + 2 * WJ - 1) / (2 * WJ), ti_n = (P.res + 2 * WI - 1) / (2 * WI);
+        const int tiles = ti_n * tj_n;
+        const int b = blockIdx.x;
+        view = b / tiles;
+        const int t = b - view * tiles;
+        const int ti = t / tj_n, tj = t - ti * tj_n;
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        i = ti * (2 * WI) + (w >> 1) * WI + lane / WJ;
+        j = tj * (2 * WJ) + (w & 1) * WJ + lane % WJ;
+    }
     const bool valid = i < P.res && j < P.res;
     if (!valid) { i = 0; j = 0; }
     const Ray64 ray = make_ray(P.cams[view], i, j, P.res);
@@ -230,17 +244,24 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     // by dw = du*ds per sample and the number of samples before the ray leaves the cell is
     // ceil(min_i dist_i/|dw_i|), dist_i = distance to the exit face = 0.5 - (w_i - 0.5)*sign(dw_i).
     // A face sample charged to the "wrong" side is evaluated 1e-6 outside its cell: same value to 1e-6.
+    // The interpolant restricted to a straight ray is a cubic in the step index q inside one cell, so the n samples
+    // of a cell sum in closed form (c0*n + c1*S1 + c2*S2 + c3*S3, S_p = sum q^p): no per-sample loop, no divergence.
     const float dwx = dux * P.ds_f, dwy = duy * P.ds_f, dwz = duz * P.ds_f;
+    const float dxy = dwx * dwy, dxz = dwx * dwz, dyz = dwy * dwz, dxyz = dwx * dwy * dwz;
+    // sample parameter t_k = s_k - R without the table: t0 + (k - kref)*ds, ds split hi + lo (half an ulp, like the table)
+    const int kref = P.n_steps >> 1;
+    const float t0 = P.t_tab[kref];
+    const float ds_lo = (float)(P.ds - (double)P.ds_f);
     const float ivx = fabsf(dwx) > 1e-12f ? 1.0f / dwx : 0.0f, hvx = fabsf(dwx) > 1e-12f ? 0.5f / fabsf(dwx) : 1e30f;
     const float ivy = fabsf(dwy) > 1e-12f ? 1.0f / dwy : 0.0f, hvy = fabsf(dwy) > 1e-12f ? 0.5f / fabsf(dwy) : 1e30f;
     const float ivz = fabsf(dwz) > 1e-12f ? 1.0f / dwz : 0.0f, hvz = fabsf(dwz) > 1e-12f ? 0.5f / fabsf(dwz) : 1e30f;
     float acc = 0.0f, cmp = 0.0f;  // Kahan over per-cell partial sums
     int k = m0;
     const int kend = hit ? m1 : m0;
-    const float* __restrict__ ttab = P.t_tab;
     while (__any_sync(FULL_MASK, k < kend)) {
         const bool live = k < kend;
-        const float t = ttab[live ? k : 0];
+        const float kf = (float)(k - kref);
+        const float t = fmaf(kf, P.ds_f, fmaf(kf, ds_lo, t0));
         const float vx = fmaf(dux, t, vcx), vy = fmaf(duy, t, vcy), vz = fmaf(duz, t, vcz);
         const float rx = vx + kMagic, ry = vy + kMagic, rz = vz + kMagic;  // cell id (as magic floats)
         const float fx = rx - kMagic, fy = ry - kMagic, fz = rz - kMagic;  // cell origin (integers)
@@ -252,18 +273,25 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
         if (live) {
             const float steps = fminf(fmaf(0.5f - wx, ivx, hvx), fminf(fmaf(0.5f - wy, ivy, hvy), fmaf(0.5f - wz, ivz, hvz)));
             const int n = max(1, min(kend - k, __float2int_ru(fminf(steps, 1.0e6f))));
-            // z-lerp differences once per cell
-            const float d00 = b.w - a.w, d01 = b.z - a.z, d10 = b.x - a.x, d11 = b.y - a.y;
-            float part = 0.0f;
-            for (int q = 0; q < n; ++q) {
-                const float v00 = fmaf(wz, d00, a.w), v01 = fmaf(wz, d01, a.z);  // x0: y0, y1
-                const float v10 = fmaf(wz, d10, a.x), v11 = fmaf(wz, d11, a.y);  // x1: y0, y1
-                const float v0 = fmaf(wy, v01 - v00, v00), v1 = fmaf(wy, v11 - v10, v10);
-                part += fmaf(wx, v1 - v0, v0);
-                wx += dwx;
-                wy += dwy;
-                wz += dwz;
-            }
+            // f = v000 + ax X + ay Y + az Z + axy XY + axz XZ + ayz YZ + axyz XYZ on the cell's corners
+            const float v000 = a.w, v010 = a.z, v100 = a.x, v110 = a.y, v001 = b.w, v011 = b.z, v101 = b.x, v111 = b.y;
+            const float ax = v100 - v000, ay = v010 - v000, az = v001 - v000;
+            const float bx = v101 - v001;
+            const float axy = (v110 - v010) - ax, axz = bx - ax, ayz = (v011 - v001) - ay;
+            const float axyz = ((v111 - v011) - bx) - axy;
+            const float tx = fmaf(wy, axyz, axz), ty = fmaf(wx, axyz, ayz), tz = fmaf(wz, axyz, axy);  // mixed partials
+            const float gx = fmaf(wz, tx, fmaf(wy, axy, ax));                                           // gradient at the
+            const float gy = fmaf(wz, ty, fmaf(wx, axy, ay));                                           // first sample
+            const float gz = fmaf(wy, ty, fmaf(wx, axz, az));
+            const float c0 = fmaf(wx, gx, fmaf(wy, fmaf(wz, ayz, ay), fmaf(wz, az, v000)));
+            const float c1 = fmaf(dwx, gx, fmaf(dwy, gy, dwz * gz));
+            const float c2 = fmaf(dxy, tz, fmaf(dxz, tx, dyz * ty));
+            const float c3 = axyz * dxyz;
+            const float nf = (float)n;
+            const float S1 = 0.5f * nf * (nf - 1.0f);
+            const float S2 = S1 * fmaf(2.0f, nf, -1.0f) * 0.333333343f;
+            const float S3 = S1 * S1;
+            const float part = fmaf(c3, S3, fmaf(c2, S2, fmaf(c1, S1, c0 * nf)));
             k += n;
             const float y_ = part - cmp;
             const float t_ = acc + y_;
@@ -274,7 +302,13 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     if (hit) n_eval += (unsigned int)(m1 - m0);
     tot += (double)acc - (double)cmp;
     const double T = P.flat_field + P.ds * (tot * P.dm);
-    store_pixel(P, view, i, j, valid, exp(-T));
+    if (WJ % 4 == 0) {
+        store_pixel(P, view, i, j, valid, exp(-T));
+    } else if (valid) {  // narrow warp footprints: lanes 4q..4q+3 are not 4 consecutive j
+        const size_t idx = ((size_t)view * P.res + i) * P.res + j;
+        if (P.out_f64) reinterpret_cast<double*>(P.out)[idx] = exp(-T);
+        else reinterpret_cast<float*>(P.out)[idx] = (float)exp(-T);
+    }
     add_stats(P, valid ? (unsigned long long)P.n_steps : 0ull, n_eval, n_fallback, n_eval, valid ? 1ull : 0ull);
 }
 
@@ -287,12 +321,29 @@ cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz
     return cudaGetLastError();
 }
 
-cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                     cudaStream_t stream) {
-    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+template <int WI, int WJ>
+static cudaError_t launch_tex_shape(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
+                                    cudaStream_t stream) {
+    const size_t ti = (size_t)(P.res + 2 * WI - 1) / (2 * WI), tj = (size_t)(P.res + 2 * WJ - 1) / (2 * WJ);
+    const size_t grid = (size_t)P.n_views * ti * tj;
     if (grid == 0) return cudaSuccess;
-    render_volume_tex_kernel<<<grid, kBlockThreads, 0, stream>>>(P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz, kVolumeGuardTol);
+    if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
+    render_volume_tex_kernel<WI, WJ><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz,
+                                                                                       kVolumeGuardTol);
     return cudaGetLastError();
+}
+
+// warp_shape: 0 = 4 x 8 pixels (i x j), 1 = 32 x 1, 2 = 1 x 32, 3 = 16 x 2, 4 = 2 x 16, 5 = 8 x 4
+cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
+                                     int warp_shape, cudaStream_t stream) {
+    switch (warp_shape) {
+        case 1: return launch_tex_shape<32, 1>(tex, d_vol, nx, ny, nz, P, stream);
+        case 2: return launch_tex_shape<1, 32>(tex, d_vol, nx, ny, nz, P, stream);
+        case 3: return launch_tex_shape<16, 2>(tex, d_vol, nx, ny, nz, P, stream);
+        case 4: return launch_tex_shape<2, 16>(tex, d_vol, nx, ny, nz, P, stream);
+        case 5: return launch_tex_shape<8, 4>(tex, d_vol, nx, ny, nz, P, stream);
+        default: return launch_tex_shape<4, 8>(tex, d_vol, nx, ny, nz, P, stream);
+    }
 }
 
 }  // namespace xr
