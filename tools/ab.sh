@@ -1,6 +1,6 @@
 #!/bin/bash
 # Development aid: A/B two builds of the library on the same box.  usage: tools/ab.sh "lattice gyroid_sigmoid" libA.so libB.so
-for rep in 1 2; do
+for rep in 1; do
 for w in $1; do
   for lib in "${@:2}"; do
     XRAY_CUDA_LIB=$PWD/$lib python bench.py --workload $w --views 8 --steps 5 --warmup 3 --no-cpu --no-ref-cuda 2>&1 | tail -1 | python -c "

@@ -58,7 +58,11 @@ struct RenderParams {
 };
 
 constexpr int kBlockThreads = 128;
-constexpr int kTileI = 8, kTileJ = 16;  // CTA tile in pixels; warp tile 4 (i) x 8 (j)
+#ifndef XR_WARP_I
+#define XR_WARP_I 4
+#endif
+constexpr int kWarpI = XR_WARP_I, kWarpJ = 32 / XR_WARP_I;  // warp tile in pixels (i x j); j is the fast output index
+constexpr int kTileI = 2 * kWarpI, kTileJ = 2 * kWarpJ;     // CTA tile: 2 x 2 warps
 constexpr int kQueueCap = 8;            // deferred refinements per lane before a flush
 
 }  // namespace xr

@@ -725,8 +725,8 @@ __device__ __forceinline__ void pixel_of_thread(const RenderParams& P, int& view
     const int t = b - view * tiles;
     const int ti = t / P.tiles_j, tj = t - ti * P.tiles_j;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    i = ti * kTileI + (w >> 1) * 4 + (lane >> 3);
-    j = tj * kTileJ + (w & 1) * 8 + (lane & 7);
+    i = ti * kTileI + (w >> 1) * kWarpI + lane / kWarpJ;
+    j = tj * kTileJ + (w & 1) * kWarpJ + lane % kWarpJ;
 }
 
 // Stage instruction stream + fp32 pool in shared memory (warp-uniform LDS broadcasts).
@@ -767,7 +767,7 @@ __device__ __forceinline__ void store_pixel(const RenderParams& P, int view, int
     float v2 = __shfl_down_sync(FULL_MASK, v, 2);
     float v3 = __shfl_down_sync(FULL_MASK, v, 3);
     float* out = reinterpret_cast<float*>(P.out);
-    if ((P.res & 3) == 0) {
+    if (kWarpJ % 4 == 0 && (P.res & 3) == 0) {
         if ((threadIdx.x & 3) == 0 && valid) *reinterpret_cast<float4*>(out + idx) = make_float4(v, v1, v2, v3);
     } else if (valid) {
         out[idx] = v;
