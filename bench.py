@@ -395,12 +395,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "algorithmic_flops_per_launch": alg_flops / max(1.0, launches), "avg_launch_ms": kernel_ms,
             "flops_model": {"per_evaluated_sample": per_sample, "per_primitive_test": per_prim},
             "evaluated_samples": evaluated, "primitive_tests": prim_tests, "fp64_fallbacks": fallbacks}
+    try:  # DRAM traffic of this kernel per launch, from the committed ncu capture of the same workload
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_dram_traffic_r1.json")))[args.workload]
+        roof["traffic"] = tr["dram_bytes_per_view"] * (views * world * args.steps / max(1.0, launches))
+        roof["traffic_source"] = tr["capture"] + " (per view) x views per launch"
+    except (OSError, KeyError, ValueError):
+        pass
     if is_volume:
         tap_bytes = evaluated * 32.0
         roof.update({"bound": "l1", "achieved": tap_bytes / world / secs / 1e9, "unit": "GB/s",
                      "peak": 128.0 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None})
         roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
-        roof["peak_source"] = "L1/shared 128 B/clk/SM x 148 SM x measured SM clock (tap stream is served on chip, HBM is <5% utilised)"
+        roof["peak_source"] = ("L1/shared 128 B/clk/SM x 148 SM x measured SM clock (tap stream is served on chip, HBM is <5% utilised); "
+                               "the unit that saturates first is texture write-back (ncu: l1tex__tex_writeback_active 89 %)")
     line = {
         "metric": "Gsamples/s", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -287,7 +287,9 @@ struct DevCtx {
     size_t img_cap = 0;
     unsigned char* h_pin[2] = {nullptr, nullptr};
     size_t pin_cap = 0;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // batch b has reached host memory (recorded on copy_stream)
+    cudaEvent_t evk[2] = {nullptr, nullptr};  // batch b's kernel is done (recorded on the compute stream)
+    cudaStream_t copy_stream = nullptr;       // D2H of batch b overlaps the kernel of batch b + 1
     CamDev* h_cams = nullptr;  // pinned staging for the camera upload
     size_t h_cams_cap = 0;
     // voxel volume as a layered 2D array (layers = z, width = y, height = x) for texture gather
@@ -326,14 +328,20 @@ static void ctx_release(DevCtx* c) {
         if (c->d_img[b]) cudaFree(c->d_img[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
         if (c->ev[b]) cudaEventDestroy(c->ev[b]);
+        if (c->evk[b]) cudaEventDestroy(c->evk[b]);
     }
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
+    c->copy_stream = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);
     c->stream = nullptr;
     c->d_cams = nullptr; c->cams_cap = 0;
     c->d_s = nullptr; c->d_t = nullptr; c->d_nfine = nullptr; c->tab_cap = 0; c->tab_integ = -1;
     c->d_stats = nullptr;
     c->h_cams = nullptr; c->h_cams_cap = 0;
-    for (int b = 0; b < 2; ++b) { c->d_img[b] = nullptr; c->h_pin[b] = nullptr; c->ev[b] = nullptr; }
+    for (int b = 0; b < 2; ++b) { c->d_img[b] = nullptr; c->h_pin[b] = nullptr; c->ev[b] = nullptr; c->evk[b] = nullptr; }
     c->img_cap = 0; c->pin_cap = 0;
 }
 
@@ -521,7 +529,8 @@ static int run_job(Job& J) {
         }
     }
 
-    const size_t max_batch_bytes = (size_t)256 << 20;
+    // host output: small batches, the un-overlapped tail is one batch of D2H; device output: fewer launches
+    const size_t max_batch_bytes = J.out_on_device ? (size_t)1 << 30 : (size_t)64 << 20;
     int max_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nv, max_batch_bytes / img_bytes));
     unsigned long long n_launches = 0;
     auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
@@ -576,8 +585,12 @@ static int run_job(Job& J) {
             for (int b = 0; b < 2; ++b) CUJ(3, cudaMallocHost(&C->h_pin[b], need));
             C->pin_cap = need;
         }
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 2; ++b) {
             if (!C->ev[b]) CUJ(3, cudaEventCreateWithFlags(&C->ev[b], cudaEventDisableTiming));
+            if (!C->evk[b]) CUJ(3, cudaEventCreateWithFlags(&C->evk[b], cudaEventDisableTiming));
+        }
+        if (!C->copy_stream) CUJ(3, cudaStreamCreateWithFlags(&C->copy_stream, cudaStreamNonBlocking));
+        cudaStream_t cstream = C->copy_stream;
         int pend_v0[2] = {0, 0}, pend_n[2] = {0, 0};
         auto drain = [&](int b) -> cudaError_t {  // copy batch b from pinned staging into the caller's buffer
             if (pend_n[b] == 0) return cudaSuccess;
@@ -595,6 +608,8 @@ static int run_job(Job& J) {
             int n = std::min(max_batch, nv - v);
             CUJ(7, drain(b));  // buffer b is free again once its previous batch reached the caller
             CUJ(5, launch(v, n, C->d_img[b]));
+            CUJ(7, cudaEventRecord(C->evk[b], stream));
+            CUJ(7, cudaStreamWaitEvent(cstream, C->evk[b], 0));
             if (out_pinned) {
                 // contiguous runs of views go out in one copy each
                 int k = 0;
@@ -602,13 +617,13 @@ static int run_job(Job& J) {
                     int m = 1;
                     while (k + m < n && J.views[v + k + m] == J.views[v + k + m - 1] + 1) ++m;
                     CUJ(8, cudaMemcpyAsync((unsigned char*)J.out + (size_t)J.views[v + k] * img_bytes,
-                                           C->d_img[b] + (size_t)k * img_bytes, (size_t)m * img_bytes, cudaMemcpyDeviceToHost, stream));
+                                           C->d_img[b] + (size_t)k * img_bytes, (size_t)m * img_bytes, cudaMemcpyDeviceToHost, cstream));
                     k += m;
                 }
             } else {
-                CUJ(8, cudaMemcpyAsync(C->h_pin[b], C->d_img[b], (size_t)n * img_bytes, cudaMemcpyDeviceToHost, stream));
+                CUJ(8, cudaMemcpyAsync(C->h_pin[b], C->d_img[b], (size_t)n * img_bytes, cudaMemcpyDeviceToHost, cstream));
             }
-            CUJ(7, cudaEventRecord(C->ev[b], stream));
+            CUJ(7, cudaEventRecord(C->ev[b], cstream));
             pend_v0[b] = v;
             pend_n[b] = n;
             v += n;
