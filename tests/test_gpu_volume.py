@@ -231,3 +231,20 @@ def test_rolled_camera_and_long_cell_runs(X, O):
             c.view[k] = v[k]
     assert _render_ext_vs_oracle(X, O, vol, cams, 20, 2.0 / 16 / 60.0) <= TOL_FP32
     assert _render_ext_vs_oracle(X, O, vol, cams, 20, 2.0 / 16 / 0.7) <= TOL_FP32  # steps longer than a voxel
+
+
+def test_staged_upload_of_big_pageable_volume(X, monkeypatch):
+    """Pageable volumes of 64 MiB and more go up through the multi-threaded pinned staging pipeline
+    (api.cu upload_h2d); the image must be bit-identical to the plain cudaMemcpy path, also for a size that
+    does not divide evenly among the staging threads."""
+    rng = np.random.default_rng(5)
+    cams = X.cameras_from_angles([(20.0, 90.0), (200.0, 70.0)], R, FOV)
+    for shape in ((256, 256, 256), (257, 255, 259)):
+        vol = rng.random(shape, dtype=np.float32)
+        ds = 2.0 / 256 / 2.0
+        img_staged = X.render_volume(vol, cams, 32, integration="simple", precision="fp32", ds=ds)
+        monkeypatch.setenv("XRAY_NO_STAGED_UPLOAD", "1")
+        img_plain = X.render_volume(vol, cams, 32, integration="simple", precision="fp32", ds=ds)
+        monkeypatch.delenv("XRAY_NO_STAGED_UPLOAD")
+        assert np.array_equal(img_staged, img_plain)
+        assert img_staged.min() < 0.9  # the volume really attenuates

@@ -95,6 +95,87 @@ static void free_dev_scene(DevScene& ds) {
     ds = DevScene();
 }
 
+// ---------------------------------------------------------------------------------------
+// Host -> device upload of a big pageable buffer (the legacy ABI hands over Go heap memory, cuda_backend.go:316):
+// cudaMemcpy from pageable memory stages through one driver thread at ~10 GB/s.  Here T host threads each own a
+// contiguous slice, copy it piecewise into their own pinned double buffer and push it on their own stream, so the
+// CPU copies and the DMA overlap and the link is the limit.  Pinned sources go out in one async copy.
+// ---------------------------------------------------------------------------------------
+static std::mutex g_stage_mu;
+static const int kStageThreads = 16;
+static const size_t kStageChunk = (size_t)8 << 20;
+static void* g_stage_buf[kStageThreads][2] = {};
+static int g_stage_dev = -1;
+
+static void stage_release_locked() {
+    for (int t = 0; t < kStageThreads; ++t)
+        for (int b = 0; b < 2; ++b) {
+            if (g_stage_buf[t][b]) cudaFreeHost(g_stage_buf[t][b]);
+            g_stage_buf[t][b] = nullptr;
+        }
+    g_stage_dev = -1;
+}
+
+static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int dev, cudaStream_t stream) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    const unsigned int hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<unsigned int>(8u, std::max(1u, hw / 2));
+    if (const char* e = getenv("XRAY_STAGE_THREADS")) T = std::max(1, std::min(kStageThreads, atoi(e)));
+    if (pinned || bytes < ((size_t)64 << 20) || T < 2 || getenv("XRAY_NO_STAGED_UPLOAD"))
+        return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (g_stage_dev != dev) stage_release_locked();
+    for (int t = 0; t < T; ++t)
+        for (int b = 0; b < 2; ++b)
+            if (!g_stage_buf[t][b]) {
+                cudaError_t e = cudaMallocHost(&g_stage_buf[t][b], kStageChunk);
+                if (e != cudaSuccess) {
+                    stage_release_locked();
+                    cudaGetLastError();
+                    return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
+                }
+            }
+    g_stage_dev = dev;
+    cudaError_t e0 = cudaStreamSynchronize(stream);  // whatever was queued before must not race the side streams
+    if (e0 != cudaSuccess) return e0;
+    std::vector<cudaError_t> errs((size_t)T, cudaSuccess);
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / T) + 255) & ~(size_t)255;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+            cudaError_t e = cudaSetDevice(dev);
+            cudaStream_t st = nullptr;
+            cudaEvent_t ev[2] = {nullptr, nullptr};
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+            const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+            int b = 0;
+            for (size_t off = lo; off < hi && e == cudaSuccess; off += kStageChunk, b ^= 1) {
+                const size_t n = std::min(kStageChunk, hi - off);
+                e = cudaEventSynchronize(ev[b]);  // the previous copy out of this buffer is done (no-op the first time)
+                if (e != cudaSuccess) break;
+                memcpy(g_stage_buf[t][b], (const unsigned char*)h_src + off, n);
+                e = cudaMemcpyAsync((unsigned char*)d_dst + off, g_stage_buf[t][b], n, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+            }
+            if (st) {
+                cudaError_t e2 = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) e = e2;
+                cudaStreamDestroy(st);
+            }
+            for (int q = 0; q < 2; ++q)
+                if (ev[q]) cudaEventDestroy(ev[q]);
+            errs[(size_t)t] = e;
+        });
+    for (auto& x : th) x.join();
+    for (cudaError_t e : errs)
+        if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 // Upload (or reuse) the program and voxel data on the current device.
 // borrowed_vox: optional device pointer to use for slot 0 instead of host data.
 // peer_dev >= 0: voxel data that needs (re)loading is pulled from that device's copy over NVLink
@@ -141,7 +222,7 @@ static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const v
                         src = &it->second;
                 }
                 if (src) CU(4, cudaMemcpyPeerAsync(ds.d_vox[s], dev, src->d_vox[s], peer_dev, bytes, stream));
-                else CU(4, cudaMemcpyAsync(ds.d_vox[s], vh.data, bytes, cudaMemcpyHostToDevice, stream));
+                else CU(4, upload_h2d(ds.d_vox[s], vh.data, bytes, dev, stream));
                 ds.vox_bytes[s] = bytes;
                 ds.vox_version[s] = vh.version;
             }
@@ -822,6 +903,10 @@ extern "C" {
 const char* XRayLastError(void) { return g_last_error.c_str(); }
 
 void XRayReleaseCaches(void) {
+    {
+        std::lock_guard<std::mutex> ls(g_stage_mu);
+        stage_release_locked();
+    }
     std::lock_guard<std::mutex> lk(g_ctx_mu);
     int cur = 0;
     cudaGetDevice(&cur);
