@@ -204,6 +204,7 @@ def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, d
                                                     ctypes.c_float, ctypes.c_float, fp]
         cams32 = X.to_legacy(cams)
         n = len(cams32)
+        vol_np = np.array(vol_np, copy=True)  # pageable, like the Go heap buffer the host hands over (cuda_backend.go:316)
         nz, nx, ny = vol_np.shape
         out = np.empty((n, res, res), dtype=np.float32)
         ours = np.empty((n, res, res), dtype=np.float32)
@@ -218,7 +219,7 @@ def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, d
         t0 = time.perf_counter()
         X.render_volume_legacy(vol_np, cams32, res, float(np.float32(ds)), out=ours)
         t_ours = time.perf_counter() - t0
-        return {"what": "reference cuda_backend.cu (sm_100 build) vs this library, same RenderVolumeProjectionsCUDA call, host buffers",
+        return {"what": "reference cuda_backend.cu (sm_100 build) vs this library, same RenderVolumeProjectionsCUDA call, same pageable host buffers (as the Go host passes)",
                 "reference_s": t_ref, "ours_s": t_ours, "reference_gsamples_per_s": ref_samples_per_step / t_ref / 1e9,
                 "ours_gsamples_per_s": ref_samples_per_step / t_ours / 1e9, "speedup": t_ref / t_ours,
                 "max_abs_image_diff": float(np.abs(out - ours).max()),

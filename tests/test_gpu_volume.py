@@ -248,3 +248,30 @@ def test_staged_upload_of_big_pageable_volume(X, monkeypatch):
         monkeypatch.delenv("XRAY_NO_STAGED_UPLOAD")
         assert np.array_equal(img_staged, img_plain)
         assert img_staged.min() < 0.9  # the volume really attenuates
+
+
+def test_empty_space_skipping_is_exact(X, O, monkeypatch):
+    """Bricks whose voxels are all +-0 are stepped over (render_volume.cu build_volume_occupancy): the reference
+    adds exact zeros there.  Mostly-empty volume with isolated single voxels, a thin plate and a block, -0.0
+    sprinkled in; compare against the oracle and against the same kernel with skipping disabled."""
+    rng = np.random.default_rng(21)
+    nz, nx, ny = 72, 80, 96
+    vol = np.zeros((nz, nx, ny), dtype=np.float32)
+    for _ in range(12):
+        vol[rng.integers(nz), rng.integers(nx), rng.integers(ny)] = rng.random()
+    vol[30, :, 10:50] = 0.7                      # one-voxel-thick plate
+    vol[50:60, 20:36, 64:88] = rng.random((10, 16, 24), dtype=np.float32)
+    vol[0, 0, 0] = 0.9                           # corners of the cube
+    vol[-1, -1, -1] = 0.4
+    vol[5:9, 60:70, 5:9] = -0.0
+    cams = X.cameras_from_angles([(0.0, 90.0), (33.0, 90.0), (118.0, 61.0), (270.0, 90.0)], R, FOV)
+    res, ds = 48, 2.0 / 96 / 3.0
+    err = _render_ext_vs_oracle(X, O, vol, cams, res, ds, ff=0.0)
+    assert err <= TOL_FP32
+    img, st = X.render_volume(vol, cams, res, integration="simple", precision="fp32", ds=ds, return_stats=True)
+    monkeypatch.setenv("XRAY_VOLUME_NO_SKIP", "1")
+    img0, st0 = X.render_volume(vol, cams, res, integration="simple", precision="fp32", ds=ds, return_stats=True)
+    assert np.abs(img.astype(np.float64) - img0).max() <= 1e-6
+    assert st["ref_samples"] == st0["ref_samples"]
+    assert st["evaluated_samples"] < 0.6 * st0["evaluated_samples"]  # most of the volume really is skipped
+    assert img.min() < 0.95

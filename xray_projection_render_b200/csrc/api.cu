@@ -33,8 +33,10 @@ cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator,
                                int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                     int warp_shape,
-                                     cudaStream_t stream);
+                                     int warp_shape, const unsigned char* occ, cudaStream_t stream);
+size_t volume_brick_count(int nx, int ny, int nz);
+cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
+                                   const unsigned char** result, cudaStream_t stream);
 cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
                                       const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
@@ -377,6 +379,9 @@ struct DevCtx {
     cudaArray_t vol_arr = nullptr;
     cudaTextureObject_t vol_tex = 0;
     int vol_dims[3] = {0, 0, 0};
+    // empty-space map of the volume (render_volume.cu build_volume_occupancy), two ping-pong buffers
+    unsigned char* vol_occ[2] = {nullptr, nullptr};
+    size_t vol_occ_cap = 0;
 };
 static std::mutex g_ctx_mu;
 static std::map<int, DevCtx*> g_ctx;
@@ -405,6 +410,11 @@ static void ctx_release(DevCtx* c) {
     c->vol_tex = 0;
     c->vol_arr = nullptr;
     c->vol_dims[0] = c->vol_dims[1] = c->vol_dims[2] = 0;
+    for (int b = 0; b < 2; ++b) {
+        if (c->vol_occ[b]) cudaFree(c->vol_occ[b]);
+        c->vol_occ[b] = nullptr;
+    }
+    c->vol_occ_cap = 0;
     for (int b = 0; b < 2; ++b) {
         if (c->d_img[b]) cudaFree(c->d_img[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
@@ -557,6 +567,7 @@ static int run_job(Job& J) {
     // Dedicated voxel kernel: (re)fill the layered array from the linear device volume.  Falls back to the
     // __ldg kernel when the array cannot be had (dimension limits: 2048 layers, 32768 x 32768 texels).
     bool use_tex = false;
+    const unsigned char* vol_occ = nullptr;
     if (J.fast_volume && !getenv("XRAY_VOLUME_LDG")) {
         const int vx = h->voxel_dims[0][0], vy = h->voxel_dims[0][1], vz = h->voxel_dims[0][2];
         if (vz <= 2048 && vx <= 32768 && vy <= 32768) {
@@ -595,6 +606,21 @@ static int run_job(Job& J) {
                 cp.kind = cudaMemcpyDeviceToDevice;
                 CUJ(4, cudaMemcpy3DAsync(&cp, stream));
                 use_tex = true;
+                if (!getenv("XRAY_VOLUME_NO_SKIP")) {
+                    const size_t nb = volume_brick_count(vx, vy, vz);
+                    if (nb > C->vol_occ_cap) {
+                        CUJ(7, cudaStreamSynchronize(stream));
+                        for (int b = 0; b < 2; ++b) {
+                            if (C->vol_occ[b]) cudaFree(C->vol_occ[b]);
+                            C->vol_occ[b] = nullptr;
+                        }
+                        C->vol_occ_cap = 0;
+                        if (cudaMalloc(&C->vol_occ[0], nb) == cudaSuccess && cudaMalloc(&C->vol_occ[1], nb) == cudaSuccess) C->vol_occ_cap = nb;
+                        cudaGetLastError();
+                    }
+                    if (C->vol_occ_cap >= nb)
+                        CUJ(5, build_volume_occupancy((const float*)ds->d_vox[0], vx, vy, vz, C->vol_occ[0], C->vol_occ[1], &vol_occ, stream));
+                }
             }
         }
     }
@@ -623,7 +649,7 @@ static int run_job(Job& J) {
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
-                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, v0, n), stream);
+                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, v0, n), vol_occ, stream);
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);

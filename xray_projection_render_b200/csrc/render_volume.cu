@@ -148,6 +148,62 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_fast_kernel(const
 // interpolation is continuous across cell faces, so which of two adjacent cells a face sample is
 // charged to does not matter; samples within the guard band of the cube faces still take the exact
 // fp64 routine.
+// ---- empty-space map: bricks of kBrick^3 cells whose every corner voxel is +-0, with the Chebyshev distance (in
+// bricks) to the nearest brick that is not.  A sample inside such a region is exactly 0 in the reference
+// (objects.go:826-853 interpolates zeros), so stepping over it changes nothing.  Rebuilt per call: the
+// volume's contents may have changed.
+constexpr int kBrick = 8;
+
+// one CTA per brick row (fixed brick X, Z): stream the (kBrick+1)^2 voxel rows it touches, coalesced along y
+__global__ void __launch_bounds__(256) brick_occupancy_kernel(const float* __restrict__ vol, int nx, int ny, int nz, int bnx, int bny,
+                                                              unsigned char* __restrict__ occ) {
+    extern __shared__ unsigned int s_flag[];  // one word per 32 voxels along y
+    const int bX = blockIdx.x % bnx, bZ = blockIdx.x / bnx;
+    const int nwords = (ny + 31) >> 5;
+    for (int w = threadIdx.x; w < nwords; w += blockDim.x) s_flag[w] = 0u;
+    __syncthreads();
+    const int x0 = bX * kBrick, z0 = bZ * kBrick;
+    const int x1 = min(x0 + kBrick, nx - 1), z1 = min(z0 + kBrick, nz - 1);
+    for (int z = z0; z <= z1; ++z)
+        for (int x = x0; x <= x1; ++x) {
+            const float* __restrict__ row = vol + ((size_t)z * nx + x) * ny;
+            for (int y = threadIdx.x; y < ny; y += blockDim.x) {
+                const bool nz_ = (__float_as_uint(row[y]) << 1) != 0u;  // anything but +-0 (NaN and Inf included)
+                const unsigned int m = __ballot_sync(__activemask(), nz_);
+                // lanes of a warp cover 32 consecutive y starting at a multiple of 32 (blockDim = 256, y = tid + k*256)
+                if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_flag[y >> 5], m);
+            }
+        }
+    __syncthreads();
+    for (int bY = threadIdx.x; bY < bny; bY += blockDim.x) {
+        const int y0 = bY * kBrick, y1 = min(y0 + kBrick, ny - 1);
+        bool any = false;
+        for (int y = y0; y <= y1; ++y) any = any || ((s_flag[y >> 5] >> (y & 31)) & 1u);
+        occ[((size_t)bZ * bnx + bX) * bny + bY] = any ? 0 : 255;  // 0 = occupied, 255 = empty, distance unknown yet
+    }
+}
+
+// one relaxation step of the Chebyshev distance transform: empty bricks take 1 + min over the 26 neighbours
+__global__ void brick_distance_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, int bnx, int bny, int bnz) {
+    const size_t n = (size_t)bnx * bny * bnz;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int bY = (int)(idx % bny), bX = (int)((idx / bny) % bnx), bZ = (int)(idx / ((size_t)bny * bnx));
+    unsigned int v = in[idx];
+    if (v != 0u) {
+        unsigned int m = 254u;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int z = bZ + dz, x = bX + dx, y = bY + dy;
+                    if (z < 0 || z >= bnz || x < 0 || x >= bnx || y < 0 || y >= bny) continue;  // outside the cube is empty too
+                    m = min(m, (unsigned int)in[((size_t)z * bnx + x) * bny + y]);
+                }
+        v = min(255u, m + 1u);
+    }
+    out[idx] = (unsigned char)v;
+}
+
 __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int layer, float tx, float ty) {
     float4 r;
     asm volatile("tld4.r.a2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6,%7,%7}];"
@@ -161,7 +217,8 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int laye
 template <int WI, int WJ>
 __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const RenderParams P, cudaTextureObject_t tex,
                                                                          const float* __restrict__ vol, int nx, int ny, int nz,
-                                                                         float tol) {
+                                                                         float tol, const unsigned char* __restrict__ occ, int bnx,
+                                                                         int bny) {
     static_assert(WI * WJ == 32, "one warp");
     int view, i, j;
     {  // block = 2 x 2 warps
@@ -256,6 +313,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     const float ivy = fabsf(dwy) > 1e-12f ? 1.0f / dwy : 0.0f, hvy = fabsf(dwy) > 1e-12f ? 0.5f / fabsf(dwy) : 1e30f;
     const float ivz = fabsf(dwz) > 1e-12f ? 1.0f / dwz : 0.0f, hvz = fabsf(dwz) > 1e-12f ? 0.5f / fabsf(dwz) : 1e30f;
     float acc = 0.0f, cmp = 0.0f;  // Kahan over per-cell partial sums
+    unsigned int n_skip = 0;       // samples stepped over inside empty regions
     int k = m0;
     const int kend = hit ? m1 : m0;
     while (__any_sync(FULL_MASK, k < kend)) {
@@ -272,7 +330,33 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
         const float4 b = gather_layer(tex, z1, fy + 1.0f, fx + 1.0f);
         if (live) {
             const float steps = fminf(fmaf(0.5f - wx, ivx, hvx), fminf(fmaf(0.5f - wy, ivy, hvy), fmaf(0.5f - wz, ivz, hvz)));
-            const int n = max(1, min(kend - k, __float2int_ru(fminf(steps, 1.0e6f))));
+            int n = max(1, min(kend - k, __float2int_ru(fminf(steps, 1.0e6f))));
+            const unsigned int any_bits = (__float_as_uint(a.x) | __float_as_uint(a.y) | __float_as_uint(a.z)) |
+                                          (__float_as_uint(a.w) | __float_as_uint(b.x) | __float_as_uint(b.y)) |
+                                          (__float_as_uint(b.z) | __float_as_uint(b.w));
+            float part = 0.0f;
+            if ((any_bits << 1) == 0u) {
+                // all eight corners are +-0: this cell adds nothing.  If the whole brick is empty, run to the edge of
+                // the empty region around it: cells [8(b-(d-1)), 8(b+d)) per axis, d = Chebyshev distance in bricks.
+                if (occ) {
+                    const int ix = min(nx - 1, max(0, __float_as_int(rx) - 0x4B400000));
+                    const int iy = min(ny - 1, max(0, __float_as_int(ry) - 0x4B400000));
+                    // 255 = still unknown after the 24 relaxation passes of build_volume_occupancy: at least 25
+                    const unsigned int d = min(25u, (unsigned int)occ[((size_t)(z0 >> 3) * bnx + (ix >> 3)) * bny + (iy >> 3)]);
+                    if (d != 0u) {
+                        const float reach = (float)(8u * d - 4u) * 2.0f;  // half-width of the region, times 2 (hv = 0.5/|dw|)
+                        const float cx = (float)(4 - (ix & 7)), cy = (float)(4 - (iy & 7)), cz = (float)(4 - (z0 & 7));
+                        const float run = fminf(fmaf(cx - wx, ivx, reach * hvx),
+                                                fminf(fmaf(cy - wy, ivy, reach * hvy), fmaf(cz - wz, ivz, reach * hvz)));
+                        // one step of slack: the run length is fp32 arithmetic on up to ~2000 steps
+                        const int m = min(kend - k, __float2int_rd(fminf(run, 1.0e6f)) - 1);
+                        if (m > n) {
+                            n_skip += (unsigned int)(m - n);
+                            n = m;
+                        }
+                    }
+                }
+            } else {
             // f = v000 + ax X + ay Y + az Z + axy XY + axz XZ + ayz YZ + axyz XYZ on the cell's corners
             const float v000 = a.w, v010 = a.z, v100 = a.x, v110 = a.y, v001 = b.w, v011 = b.z, v101 = b.x, v111 = b.y;
             const float ax = v100 - v000, ay = v010 - v000, az = v001 - v000;
@@ -291,7 +375,8 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
             const float S1 = 0.5f * nf * (nf - 1.0f);
             const float S2 = S1 * fmaf(2.0f, nf, -1.0f) * 0.333333343f;
             const float S3 = S1 * S1;
-            const float part = fmaf(c3, S3, fmaf(c2, S2, fmaf(c1, S1, c0 * nf)));
+            part = fmaf(c3, S3, fmaf(c2, S2, fmaf(c1, S1, c0 * nf)));
+            }
             k += n;
             const float y_ = part - cmp;
             const float t_ = acc + y_;
@@ -299,7 +384,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
             acc = t_;
         }
     }
-    if (hit) n_eval += (unsigned int)(m1 - m0);
+    if (hit) n_eval += (unsigned int)(m1 - m0) - n_skip;
     tot += (double)acc - (double)cmp;
     const double T = P.flat_field + P.ds * (tot * P.dm);
     if (WJ % 4 == 0) {
@@ -323,27 +408,51 @@ cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz
 
 template <int WI, int WJ>
 static cudaError_t launch_tex_shape(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                    cudaStream_t stream) {
+                                    const unsigned char* occ, cudaStream_t stream) {
     const size_t ti = (size_t)(P.res + 2 * WI - 1) / (2 * WI), tj = (size_t)(P.res + 2 * WJ - 1) / (2 * WJ);
     const size_t grid = (size_t)P.n_views * ti * tj;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
-    render_volume_tex_kernel<WI, WJ><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz,
-                                                                                       kVolumeGuardTol);
+    render_volume_tex_kernel<WI, WJ><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(
+        P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz, kVolumeGuardTol, occ, (nx + kBrick - 1) / kBrick, (ny + kBrick - 1) / kBrick);
     return cudaGetLastError();
 }
 
 // warp_shape: 0 = 4 x 8 pixels (i x j), 1 = 32 x 1, 2 = 1 x 32, 3 = 16 x 2, 4 = 2 x 16, 5 = 8 x 4
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                     int warp_shape, cudaStream_t stream) {
+                                     int warp_shape, const unsigned char* occ, cudaStream_t stream) {
     switch (warp_shape) {
-        case 1: return launch_tex_shape<32, 1>(tex, d_vol, nx, ny, nz, P, stream);
-        case 2: return launch_tex_shape<1, 32>(tex, d_vol, nx, ny, nz, P, stream);
-        case 3: return launch_tex_shape<16, 2>(tex, d_vol, nx, ny, nz, P, stream);
-        case 4: return launch_tex_shape<2, 16>(tex, d_vol, nx, ny, nz, P, stream);
-        case 5: return launch_tex_shape<8, 4>(tex, d_vol, nx, ny, nz, P, stream);
-        default: return launch_tex_shape<4, 8>(tex, d_vol, nx, ny, nz, P, stream);
+        case 1: return launch_tex_shape<32, 1>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        case 2: return launch_tex_shape<1, 32>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        case 3: return launch_tex_shape<16, 2>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        case 4: return launch_tex_shape<2, 16>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        case 5: return launch_tex_shape<8, 4>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        default: return launch_tex_shape<4, 8>(tex, d_vol, nx, ny, nz, P, occ, stream);
     }
+}
+
+size_t volume_brick_count(int nx, int ny, int nz) {
+    return (size_t)((nx + kBrick - 1) / kBrick) * ((ny + kBrick - 1) / kBrick) * ((nz + kBrick - 1) / kBrick);
+}
+
+// Fill occ_a with the empty-space map of d_vol (occ_b is scratch of the same size); returns the buffer holding the result.
+cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
+                                   const unsigned char** result, cudaStream_t stream) {
+    const int bnx = (nx + kBrick - 1) / kBrick, bny = (ny + kBrick - 1) / kBrick, bnz = (nz + kBrick - 1) / kBrick;
+    const size_t smem = (size_t)((ny + 31) / 32) * sizeof(unsigned int);
+    brick_occupancy_kernel<<<(unsigned int)(bnx * bnz), 256, smem, stream>>>(d_vol, nx, ny, nz, bnx, bny, occ_a);
+    const size_t n = (size_t)bnx * bny * bnz;
+    const unsigned int grid = (unsigned int)((n + 255) / 256);
+    unsigned char *src = occ_a, *dst = occ_b;
+    // 24 relaxations: distances up to 24 bricks (a 192-cell run per look-up) are exact, larger ones saturate low
+    for (int it = 0; it < 24; ++it) {
+        brick_distance_kernel<<<grid, 256, 0, stream>>>(src, dst, bnx, bny, bnz);
+        unsigned char* t = src;
+        src = dst;
+        dst = t;
+    }
+    *result = src;
+    return cudaGetLastError();
 }
 
 }  // namespace xr
