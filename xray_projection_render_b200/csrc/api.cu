@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -129,6 +130,7 @@ static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int 
     if (pinned || bytes < ((size_t)64 << 20) || T < 2 || getenv("XRAY_NO_STAGED_UPLOAD"))
         return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream);
     std::lock_guard<std::mutex> lk(g_stage_mu);
+    const auto t_begin = std::chrono::steady_clock::now();
     if (g_stage_dev != dev) stage_release_locked();
     for (int t = 0; t < T; ++t)
         for (int b = 0; b < 2; ++b)
@@ -175,6 +177,10 @@ static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int 
     for (auto& x : th) x.join();
     for (cudaError_t e : errs)
         if (e != cudaSuccess) return e;
+    if (getenv("XRAY_DEBUG_TIMING")) {
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        fprintf(stderr, "[xray] staged upload: %.1f MB in %.1f ms (%.1f GB/s, %d threads)\n", bytes / 1e6, dt * 1e3, bytes / dt / 1e9, T);
+    }
     return cudaSuccess;
 }
 
