@@ -87,7 +87,9 @@ typedef struct {
     uint32_t struct_size;      /* = sizeof(XRayRenderOpts); guards against ABI drift */
     int32_t integration;       /* XRAY_INTEGRATE_*  (reference global `integrate`, main.go:39) */
     int32_t precision;         /* XRAY_PRECISION_*: fp32 = guard-banded fp32 (|dI| <= 1e-4),
-                                  fp64 = reference operation order (|dI| <= 1e-9) */
+                                  fp64 = reference operation order (|dI| <= 1e-9).  An fp32 request is promoted to
+                                  fp64 when the cameras put o + d*R so far from the origin (distant camera with a
+                                  wide field of view) that fp32 positions would exceed the guard bands' budget. */
     int32_t out_dtype;         /* XRAY_OUT_* element type of the image buffer */
     double ds;                 /* step; <= 0 selects MinFeatureSize()/5 (main.go:350-353) */
     double flat_field;         /* reference global flat_field (main.go:40) */
