@@ -36,6 +36,9 @@ WORKLOADS = {
     "gyroid_sigmoid": ("gyroid_example.json", "deformation_sigmoid.json", 720, 1024, "hierarchical", -1.0),  # configs[2]
     "voxel1024": (None, None, 1440, 2048, "simple", -1.0),                                     # configs[3] (8 GPUs)
     "pillar_array": ("pillar_array.json", None, 2880, 4096, "hierarchical", -1.0),             # configs[4]
+    # the reference's two remaining example scenes (not BASELINE configs; regression coverage for sphere / box / pped runs)
+    "balls": ("balls.json", None, 360, 1024, "hierarchical", -1.0),
+    "box_w_pped": ("box_w_pped.json", None, 360, 1024, "hierarchical", -1.0),
 }
 R_CAM, FOV, POLAR = 4.0, 40.0, 90.0
 

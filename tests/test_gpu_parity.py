@@ -298,3 +298,27 @@ def test_far_wide_and_near_cameras(X, O, scenes, Rcam, fov, promoted):
     else:
         assert np.abs(img.astype(np.float64) - ref).max() <= TOL_FP32
         assert st["evaluated_samples"] < nref  # fp32 kernel: culled / skipped samples are not evaluated
+
+
+@pytest.mark.parametrize("name,deform,az", [("lattice", None, 90.0), ("lattice", None, 45.0), ("pillar_array", None, 0.0),
+                                            ("lattice", "deformation_linear", 90.0), ("gyroid_example", "deformation_sigmoid", 90.0)])
+def test_rays_inside_cell_face_planes(X, O, scenes, name, deform, az):
+    """polar = 90 deg puts the central pixel row in the plane z = 0, which is a unit-cell face of the lattice and the
+    pillar array: every sample of those rays sits on the fold discontinuity and the period is decided by rounding
+    noise of the fp64 reference arithmetic.  fp32 mode must reproduce it through the exact-fold cold path
+    (render_fast.cu exact_fold_cold); checked on the central row and its neighbours at full benchmark resolution."""
+    obj = str(scenes / f"{name}.json")
+    d = str(scenes / f"{deform}.json") if deform else None
+    sc, osc = X.Scene(obj, d), O.OracleScene(obj, d)
+    ds = sc.auto_ds() if name != "gyroid_example" else 0.004
+    res = 256
+    cams = X.cameras_from_angles([(az, 90.0)], R, FOV)
+    eye, cm = O.camera_from_angles(az, 90.0, R)
+    rows = (res // 2 - 1, res // 2 + 2)
+    ref, _ = osc.render_view(eye, cm, res, FOV, R, ds, "hierarchical", rows=rows)
+    img, st = X.render_scene(sc, cams, res, precision="fp32", ds=ds, return_stats=True)
+    # oracle rows index i (camera x); the degenerate direction is j = res/2 (camera y = 0): check both cuts
+    assert np.abs(img[0, rows[0]:rows[1]].astype(np.float64) - ref[rows[0]:rows[1]]).max() <= TOL_FP32
+    refT, _ = osc.render_view(eye, cm, res, FOV, R, ds, "hierarchical")
+    assert np.abs(img[0][:, res // 2 - 1:res // 2 + 2].astype(np.float64) - refT[:, res // 2 - 1:res // 2 + 2]).max() <= TOL_FP32
+    assert st["fp64_fallbacks"] > 0

@@ -792,7 +792,8 @@ static bool fp32_position_bound_ok(const Header* h, const XRayCameraParams64* ca
     for (int a = 0; a < 3; ++a) amax = std::fmax(amax, std::fmax(std::fabs(h->aabb_lo[a]), std::fabs(h->aabb_hi[a])));
     const double xmax = std::fmin(pcmax + tmax, std::isfinite(amax) ? amax + 0.01 : 1e300);  // only positions inside the scene matter
     const double base = 1.0e-6;  // kEpsPosBase (scene_compile.cpp): the budget for the un-warped position
-    if (kU32 * (2.0 * tmax + pcmax + xmax) * 1.25 > base) return false;
+    // roundings: fl(d)*t, fl(t) (coarse: the table entry; fine: t_tab[k] + j*ds_fine is rounded twice), fl(pc), the fma
+    if (kU32 * (3.0 * tmax + pcmax + xmax) * 1.25 > base) return false;
     if (h->n_deform > 0 && pcmax + tmax > 4.0) return false;  // warp error terms assume |x| <= 4 (scene_compile.cpp deform_eps_pos)
     return true;
 }
@@ -830,7 +831,7 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
 
     // fp32 mode is only sound while every sample position x = fma(fl(d), fl(s - R), fl(o + d*R)) stays within
     // the position error the guard bands were derived for (Header.eps_pos = 1e-6 x warp Lipschitz):
-    // |dx| <= u32 * (2*|t|max + |pc| + |x|).  A distant camera or a wide field of view puts pc = o + d*R far
+    // |dx| <= u32 * (3*|t|max + |pc| + |x|).  A distant camera or a wide field of view puts pc = o + d*R far
     // from the origin; such calls are promoted to the fp64 kernels (slower, always exact) instead of risking a
     // misclassified sample.
     if (opts.precision == XRAY_PRECISION_FP32 && !fp32_position_bound_ok(h, cams, n, res)) {
