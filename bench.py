@@ -163,7 +163,8 @@ def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
         osc = O.OracleScene(str(SCENES / obj), str(SCENES / deform) if deform else None)
         ds_v = osc.auto_ds() if ds <= 0 else ds
         sample_res = min(res, 256)
-    threads = nthreads or O.max_threads()
+    # all host cores this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for every rank
+    threads = nthreads or max(O.max_threads(), len(os.sched_getaffinity(0)))
     angles = O.generate_camera_angles(views)
     # calibrate on a thin strip, then size the sample for ~budget_s of CPU work
     eye, cm = O.camera_from_angles(*angles[0], R_CAM)
