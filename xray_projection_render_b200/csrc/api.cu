@@ -30,8 +30,8 @@ namespace xr {
 cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream);
 cudaError_t launch_voxelize_scene(const RenderParams& P, int res, float* d_out, cudaStream_t stream);
 cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream);
-cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, const unsigned char* d_nfine,
-                               int i_coll, int i_tess, cudaStream_t stream);
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
+                               const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
                                      int warp_shape, const unsigned char* occ, cudaStream_t stream);
@@ -633,9 +633,14 @@ static int run_job(Job& J) {
 
     // big collections carry a cell-list grid: their fp32 pool stays in global memory (only instructions are staged)
     bool use_list = false;
+    int single_prim = 0;  // OP_CYL / OP_GYROID when the (collection of the) scene is exactly one such primitive
     if (shape != 0) {
         const Instr* I = (const Instr*)(J.scene->blob.data() + h->instr_off);
         use_list = I[i_coll].op == OP_COLL_BEGIN && (I[i_coll].flags & F_HAS_LIST);
+        const int rb = I[i_coll].op == OP_COLL_BEGIN ? i_coll + 1 : i_coll;
+        const int re = I[i_coll].op == OP_COLL_BEGIN ? (int)I[i_coll].skip_to : i_coll + 1;
+        if (!use_list && re - rb == 1 && I[rb].n == 1 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID) && !getenv("XRAY_NO_SINGLE_PRIM"))
+            single_prim = (int)I[rb].op;
         if (use_list && J.opts.precision == XRAY_PRECISION_FP32) {
             P.prog_in_smem = 0;
             P.smem_prog_bytes = (unsigned int)((size_t)h->n_instr * sizeof(Instr));
@@ -660,7 +665,8 @@ static int run_job(Job& J) {
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
         if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && (P.prog_in_smem || use_list) && fast_kernel_smem_bytes(P) <= 200 * 1024)
-            return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, use_list, C->d_nfine, i_coll, i_tess, stream);
+            return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, use_list, single_prim, C->d_nfine, i_coll, i_tess,
+                                      stream);
         return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
     };
 

@@ -204,6 +204,29 @@ finish:
     return val;
 }
 
+// Collections (or bare scenes) that are ONE primitive -- a gyroid unit cell, a pillar array -- skip the run decoding,
+// the candidate loop and its votes altogether (objects.go:422-438 for a single child: greedy returns a positive
+// rho unclamped, otherwise the "sum" is that one rho, clamped to [0,1] when the parent is a collection).
+template <int PRIM, bool COUNT>
+__device__ __forceinline__ float eval_single(const float4* __restrict__ q, unsigned int cflags, float x, float y, float z, bool alive,
+                                             bool& unc, unsigned int& prim_tests, float& clr) {
+    bool in, near;
+    float rho;
+    if (PRIM == OP_GYROID) {
+        float margin;
+        prim_gyroid(q, x, y, z, in, near, rho, margin);
+        if (alive) clr = fminf(clr, margin);
+    } else {
+        prim_cyl(q, x, y, z, in, near, rho);
+        clr = 0.0f;
+    }
+    if (COUNT) prim_tests += alive ? 1u : 0u;
+    unc = unc || (near && alive);
+    float val = (in && alive) ? rho : 0.0f;
+    if ((cflags & 0x100u) && !((cflags & F_GREEDY) && rho > 0.0f)) val = __saturatef(val);
+    return val;
+}
+
 // Big collections (> 63 primitive children): every lane owns the ascending child list [lp, le) of its grid
 // cell; a warp min-reduction merges the lists, so the union is visited in child order and each candidate
 // is tested once by the whole warp (parameters through __ldg: uniform address, one L1 sector).
@@ -241,7 +264,7 @@ __device__ __forceinline__ float eval_list(const float4* __restrict__ F, const u
     return val;
 }
 
-template <int SHAPE, int INTEG, bool COUNT, bool LIST>
+template <int SHAPE, int INTEG, bool COUNT, bool LIST, int PRIM>
 __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
                                                                        int i_coll, int i_tess) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -312,6 +335,7 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
     const unsigned int cflags = is_coll ? (cw0.z | 0x100u) : 0u;
     const bool has_grid = LIST || (is_coll && (cw0.z & F_HAS_GRID));
     const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
+    const float4* q1 = sF + reinterpret_cast<const uint4*>(sI + rb)[1].x;  // PRIM != 0: the one primitive's record
     const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
     // cell-list grid sub-arrays (LIST): offsets are in the 5th record word, relative to `grids`
     const uint4 lb = LIST ? *reinterpret_cast<const uint4*>(gF + 4) : make_uint4(0u, 0u, 0u, 0u);
@@ -479,6 +503,7 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
         const bool evaluated = (um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive);
         if (evaluated) {
             if (LIST) rho = eval_list<COUNT>(sF, l_tab, l_idx, lp, le, cflags, x, y, z, alive, unc, prim_tests);
+            else if (PRIM != 0) rho = eval_single<PRIM, COUNT>(q1, cflags, x, y, z, alive, unc, prim_tests, clr);
             else rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
         }
         if (evaluated && !has_grid && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
@@ -550,10 +575,10 @@ size_t fast_kernel_smem_bytes(const RenderParams& P) {
     return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double) + (size_t)kQueueCap * kBlockThreads * sizeof(int);
 }
 
-template <int SHAPE, int INTEG, bool COUNT, bool LIST>
+template <int SHAPE, int INTEG, bool COUNT, bool LIST, int PRIM>
 static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine, int i_coll, int i_tess, size_t smem, unsigned int grid,
                               cudaStream_t stream) {
-    auto kern = render_fast_kernel<SHAPE, INTEG, COUNT, LIST>;
+    auto kern = render_fast_kernel<SHAPE, INTEG, COUNT, LIST, PRIM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kBlockThreads, smem, stream>>>(P, nfine, i_coll, i_tess);
@@ -562,16 +587,24 @@ static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine,
 
 // shape: SHAPE_FLAT / SHAPE_TESS; i_coll: index of the COLL_BEGIN (or of the lone primitive run);
 // i_tess: index of the TESS_BEGIN.
-cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, const unsigned char* d_nfine,
-                               int i_coll, int i_tess, cudaStream_t stream) {
+// prim: OP_CYL / OP_GYROID when the collection is exactly that one primitive (specialised variants), else 0.
+cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
+                               const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream) {
     const size_t smem = fast_kernel_smem_bytes(P);
     const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
     if (grid == 0) return cudaSuccess;
-#define XR_GO(S, I, C, L) return launch_one<S, I, C, L>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
-#define XR_PICK(S, I)                                      \
-    do {                                                   \
-        if (count) { if (list) XR_GO(S, I, true, true); else XR_GO(S, I, true, false); } \
-        else { if (list) XR_GO(S, I, false, true); else XR_GO(S, I, false, false); }     \
+#define XR_GO(S, I, C, L, Q) return launch_one<S, I, C, L, Q>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
+#define XR_PICK2(S, I, C)                                              \
+    do {                                                               \
+        if (list) XR_GO(S, I, C, true, 0);                             \
+        else if (prim == (int)OP_CYL) XR_GO(S, I, C, false, (int)OP_CYL);       \
+        else if (prim == (int)OP_GYROID) XR_GO(S, I, C, false, (int)OP_GYROID); \
+        else XR_GO(S, I, C, false, 0);                                 \
+    } while (0)
+#define XR_PICK(S, I)                      \
+    do {                                   \
+        if (count) XR_PICK2(S, I, true);   \
+        else XR_PICK2(S, I, false);        \
     } while (0)
     if (shape == SHAPE_FLAT) {
         if (integrator == 0) XR_PICK(SHAPE_FLAT, 0);
@@ -581,6 +614,7 @@ cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator,
         else XR_PICK(SHAPE_TESS, 1);
     }
 #undef XR_PICK
+#undef XR_PICK2
 #undef XR_GO
     return cudaErrorInvalidValue;
 }
