@@ -639,7 +639,8 @@ static int run_job(Job& J) {
         use_list = I[i_coll].op == OP_COLL_BEGIN && (I[i_coll].flags & F_HAS_LIST);
         const int rb = I[i_coll].op == OP_COLL_BEGIN ? i_coll + 1 : i_coll;
         const int re = I[i_coll].op == OP_COLL_BEGIN ? (int)I[i_coll].skip_to : i_coll + 1;
-        if (!use_list && re - rb == 1 && I[rb].n == 1 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID) && !getenv("XRAY_NO_SINGLE_PRIM"))
+        if (!use_list && re - rb == 1 && I[rb].child_bit == 0 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID) &&
+            !getenv("XRAY_NO_SINGLE_PRIM"))
             single_prim = (int)I[rb].op;
         if (use_list && J.opts.precision == XRAY_PRECISION_FP32) {
             P.prog_in_smem = 0;

@@ -208,8 +208,33 @@ finish:
 // the candidate loop and its votes altogether (objects.go:422-438 for a single child: greedy returns a positive
 // rho unclamped, otherwise the "sum" is that one rho, clamped to [0,1] when the parent is a collection).
 template <int PRIM, bool COUNT>
-__device__ __forceinline__ float eval_single(const float4* __restrict__ q, unsigned int cflags, float x, float y, float z, bool alive,
+__device__ __forceinline__ float eval_single(const float4* __restrict__ q, unsigned int n, unsigned int cflags, bool has_mask,
+                                             unsigned int umask_lo, unsigned int umask_hi, float x, float y, float z, bool alive,
                                              bool& unc, unsigned int& prim_tests, float& clr) {
+    if (n != 1u) {
+        // one run of n like primitives (a strut lattice): the candidate loop without run decoding or type dispatch
+        const bool greedy = (cflags & F_GREEDY) != 0;
+        float acc = 0.0f, res = alive ? 0.0f : -1.0f;
+        int nhit = 0;
+        unsigned long long bits = n >= 64u ? ~0ull : ((1ull << n) - 1ull);
+        if (has_mask) bits &= ((unsigned long long)umask_hi << 32) | umask_lo;
+        const unsigned int lo = (unsigned int)bits, hi = (unsigned int)(bits >> 32);
+        if (PRIM == OP_GYROID) {
+            XR_FOR_EACH_CHILD(lo, hi, {
+                float margin;
+                prim_gyroid(q + c * kF32Gyroid, x, y, z, in, near, rho, margin);
+                if (res == 0.0f) clr = fminf(clr, margin);
+            })
+        } else {
+            XR_FOR_EACH_CHILD(lo, hi, { prim_cyl(q + c * kF32Cyl, x, y, z, in, near, rho); clr = 0.0f; })
+        }
+    finish:
+        float val = acc;
+        if (cflags & 0x100u) val = __saturatef(acc);
+        if (nhit >= 2 && fabsf(acc) < 1e-5f && res == 0.0f) unc = true;
+        if (res > 0.0f) val = res;
+        return val;
+    }
     bool in, near;
     float rho;
     if (PRIM == OP_GYROID) {
@@ -335,7 +360,8 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
     const unsigned int cflags = is_coll ? (cw0.z | 0x100u) : 0u;
     const bool has_grid = LIST || (is_coll && (cw0.z & F_HAS_GRID));
     const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
-    const float4* q1 = sF + reinterpret_cast<const uint4*>(sI + rb)[1].x;  // PRIM != 0: the one primitive's record
+    const float4* q1 = sF + reinterpret_cast<const uint4*>(sI + rb)[1].x;  // PRIM != 0: the one run's records
+    const unsigned int n1 = reinterpret_cast<const uint4*>(sI + rb)[0].y;   //            and its child count
     const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
     // cell-list grid sub-arrays (LIST): offsets are in the 5th record word, relative to `grids`
     const uint4 lb = LIST ? *reinterpret_cast<const uint4*>(gF + 4) : make_uint4(0u, 0u, 0u, 0u);
@@ -503,7 +529,7 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
         const bool evaluated = (um_lo | um_hi) != 0u && __any_sync(FULL_MASK, alive);
         if (evaluated) {
             if (LIST) rho = eval_list<COUNT>(sF, l_tab, l_idx, lp, le, cflags, x, y, z, alive, unc, prim_tests);
-            else if (PRIM != 0) rho = eval_single<PRIM, COUNT>(q1, cflags, x, y, z, alive, unc, prim_tests, clr);
+            else if (PRIM != 0) rho = eval_single<PRIM, COUNT>(q1, n1, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
             else rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
         }
         if (evaluated && !has_grid && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
