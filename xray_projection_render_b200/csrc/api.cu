@@ -633,13 +633,13 @@ static int run_job(Job& J) {
 
     // big collections carry a cell-list grid: their fp32 pool stays in global memory (only instructions are staged)
     bool use_list = false;
-    int single_prim = 0;  // OP_CYL / OP_GYROID when the (collection of the) scene is exactly one such primitive
+    int single_prim = 0;  // the op when the (collection of the) scene is exactly one run of cylinders / gyroids / spheres / boxes
     if (shape != 0) {
         const Instr* I = (const Instr*)(J.scene->blob.data() + h->instr_off);
         use_list = I[i_coll].op == OP_COLL_BEGIN && (I[i_coll].flags & F_HAS_LIST);
         const int rb = I[i_coll].op == OP_COLL_BEGIN ? i_coll + 1 : i_coll;
         const int re = I[i_coll].op == OP_COLL_BEGIN ? (int)I[i_coll].skip_to : i_coll + 1;
-        if (!use_list && re - rb == 1 && I[rb].child_bit == 0 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID) &&
+        if (!use_list && re - rb == 1 && I[rb].child_bit == 0 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID || I[rb].op == OP_SPHERE || I[rb].op == OP_BOX) &&
             !getenv("XRAY_NO_SINGLE_PRIM"))
             single_prim = (int)I[rb].op;
         if (use_list && J.opts.precision == XRAY_PRECISION_FP32) {

@@ -225,6 +225,10 @@ __device__ __forceinline__ float eval_single(const float4* __restrict__ q, unsig
                 prim_gyroid(q + c * kF32Gyroid, x, y, z, in, near, rho, margin);
                 if (res == 0.0f) clr = fminf(clr, margin);
             })
+        } else if (PRIM == OP_SPHERE) {
+            XR_FOR_EACH_CHILD(lo, hi, { prim_sphere(q + c * kF32Sphere, x, y, z, in, near, rho); clr = 0.0f; })
+        } else if (PRIM == OP_BOX) {
+            XR_FOR_EACH_CHILD(lo, hi, { prim_box(q + c * kF32Box, x, y, z, in, near, rho); clr = 0.0f; })
         } else {
             XR_FOR_EACH_CHILD(lo, hi, { prim_cyl(q + c * kF32Cyl, x, y, z, in, near, rho); clr = 0.0f; })
         }
@@ -242,7 +246,9 @@ __device__ __forceinline__ float eval_single(const float4* __restrict__ q, unsig
         prim_gyroid(q, x, y, z, in, near, rho, margin);
         if (alive) clr = fminf(clr, margin);
     } else {
-        prim_cyl(q, x, y, z, in, near, rho);
+        if (PRIM == OP_SPHERE) prim_sphere(q, x, y, z, in, near, rho);
+        else if (PRIM == OP_BOX) prim_box(q, x, y, z, in, near, rho);
+        else prim_cyl(q, x, y, z, in, near, rho);
         clr = 0.0f;
     }
     if (COUNT) prim_tests += alive ? 1u : 0u;
@@ -613,7 +619,7 @@ static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine,
 
 // shape: SHAPE_FLAT / SHAPE_TESS; i_coll: index of the COLL_BEGIN (or of the lone primitive run);
 // i_tess: index of the TESS_BEGIN.
-// prim: OP_CYL / OP_GYROID when the collection is exactly that one primitive (specialised variants), else 0.
+// prim: OP_CYL / OP_GYROID / OP_SPHERE / OP_BOX when the collection is exactly one run of that type (specialised variants), else 0.
 cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
                                const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream) {
     const size_t smem = fast_kernel_smem_bytes(P);
@@ -625,6 +631,8 @@ cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator,
         if (list) XR_GO(S, I, C, true, 0);                             \
         else if (prim == (int)OP_CYL) XR_GO(S, I, C, false, (int)OP_CYL);       \
         else if (prim == (int)OP_GYROID) XR_GO(S, I, C, false, (int)OP_GYROID); \
+        else if (prim == (int)OP_SPHERE) XR_GO(S, I, C, false, (int)OP_SPHERE); \
+        else if (prim == (int)OP_BOX) XR_GO(S, I, C, false, (int)OP_BOX);       \
         else XR_GO(S, I, C, false, 0);                                 \
     } while (0)
 #define XR_PICK(S, I)                      \
