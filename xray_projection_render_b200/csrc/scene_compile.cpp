@@ -739,7 +739,9 @@ static double deform_eps_pos(const std::vector<Deform>& ds, double* lip_out = nu
             case D_RIGID: add = 4 * kU32 * 4.0; break;
             case D_SIGMOID:
                 lip = 1.0 + std::fabs(d.d[0] / (4.0 * d.d[2]));
-                add = std::fabs(d.d[0]) * 2e-6 + 4 * kU32 * 4.0;
+                // A*sigma through __expf (2 + 1.173|a| ulp on e, damped by sigma(1-sigma) <= e^-|a|) and __fdividef (2 ulp):
+                // <= 4e-7 |A|; budget 1e-6 |A|.  Plus the rounding of the final add at |x| <= 4 (api.cu checks the cameras).
+                add = std::fabs(d.d[0]) * 1e-6 + 2 * kU32 * 4.0;
                 break;
             case D_GAUSSIAN: {
                 double g = 0.0, a = 0.0;
