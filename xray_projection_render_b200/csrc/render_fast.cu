@@ -296,7 +296,10 @@ __device__ __forceinline__ float eval_list(const float4* __restrict__ F, const u
 }
 
 template <int SHAPE, int INTEG, bool COUNT, bool LIST, int PRIM>
-__global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
+#ifndef XR_FAST_MINBLOCKS
+#define XR_FAST_MINBLOCKS 7  // 72 registers: the best of the 6 / 7 / 8 sweep on every bench scene
+#endif
+__global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
                                                                        int i_coll, int i_tess) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles] [queue kQueueCap x nt ints]
@@ -538,7 +541,9 @@ __global__ void __launch_bounds__(kBlockThreads, 7) render_fast_kernel(const Ren
             else if (PRIM != 0) rho = eval_single<PRIM, COUNT>(q1, n1, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
             else rho = eval_runs<COUNT>(sI, sF, rb, re, cflags, has_grid, um_lo, um_hi, x, y, z, alive, unc, prim_tests, clr);
         }
-        if (evaluated && !has_grid && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
+        if (!has_grid) {  // uniform: scenes with a grid never pay for the margin arithmetic
+            if (evaluated && alive) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
+        }
         rho *= dmf;
         unc = unc && act;
         if (__any_sync(FULL_MASK, unc)) {
