@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_fast_kernel(const
 // (objects.go:826-853 interpolates zeros), so stepping over it changes nothing.  Rebuilt per call: the
 // volume's contents may have changed.
 constexpr int kBrick = 8;
+constexpr int kOccPasses = 8;  // even: the result lands back in the first ping-pong buffer
 
 // one CTA per brick row (fixed brick X, Z): stream the (kBrick+1)^2 voxel rows it touches, coalesced along y
 __global__ void __launch_bounds__(256) brick_occupancy_kernel(const float* __restrict__ vol, int nx, int ny, int nz, int bnx, int bny,
@@ -341,8 +342,8 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
                 if (occ) {
                     const int ix = min(nx - 1, max(0, __float_as_int(rx) - 0x4B400000));
                     const int iy = min(ny - 1, max(0, __float_as_int(ry) - 0x4B400000));
-                    // 255 = still unknown after the 24 relaxation passes of build_volume_occupancy: at least 25
-                    const unsigned int d = min(25u, (unsigned int)occ[((size_t)(z0 >> 3) * bnx + (ix >> 3)) * bny + (iy >> 3)]);
+                    // 255 = still unknown after the kOccPasses relaxations of build_volume_occupancy: at least one more
+                    const unsigned int d = min((unsigned int)(kOccPasses + 1), (unsigned int)occ[((size_t)(z0 >> 3) * bnx + (ix >> 3)) * bny + (iy >> 3)]);
                     if (d != 0u) {
                         const float reach = (float)(8u * d - 4u) * 2.0f;  // half-width of the region, times 2 (hv = 0.5/|dw|)
                         const float cx = (float)(4 - (ix & 7)), cy = (float)(4 - (iy & 7)), cz = (float)(4 - (z0 & 7));
@@ -444,8 +445,9 @@ cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, u
     const size_t n = (size_t)bnx * bny * bnz;
     const unsigned int grid = (unsigned int)((n + 255) / 256);
     unsigned char *src = occ_a, *dst = occ_b;
-    // 24 relaxations: distances up to 24 bricks (a 192-cell run per look-up) are exact, larger ones saturate low
-    for (int it = 0; it < 24; ++it) {
+    // kOccPasses relaxations: distances up to that many bricks (a 64-cell run per look-up) are exact, larger ones are
+    // reported as kOccPasses + 1 by the reader; a ray crossing a big void simply looks up a few more times
+    for (int it = 0; it < kOccPasses; ++it) {
         brick_distance_kernel<<<grid, 256, 0, stream>>>(src, dst, bnx, bny, bnz);
         unsigned char* t = src;
         src = dst;
