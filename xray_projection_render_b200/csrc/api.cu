@@ -37,7 +37,7 @@ cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol,
                                      int warp_shape, const unsigned char* occ, cudaStream_t stream);
 size_t volume_brick_count(int nx, int ny, int nz);
 cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
-                                   const unsigned char** result, cudaStream_t stream);
+                                   const unsigned char** result, unsigned long long surf, cudaStream_t stream);
 cudaError_t launch_voxelize_cylinders(const CylinderParams* d_cyl, int n, int res, float dm, const int* d_off,
                                       const int* d_idx, int grid_dim, float* d_out, cudaStream_t stream);
 cudaError_t measure_fp32_peak(double* tflops);
@@ -384,6 +384,7 @@ struct DevCtx {
     // voxel volume as a layered 2D array (layers = z, width = y, height = x) for texture gather
     cudaArray_t vol_arr = nullptr;
     cudaTextureObject_t vol_tex = 0;
+    cudaSurfaceObject_t vol_surf = 0;  // same array, for the fused copy + empty-space pass (0 if unavailable)
     int vol_dims[3] = {0, 0, 0};
     // empty-space map of the volume (render_volume.cu build_volume_occupancy), two ping-pong buffers
     unsigned char* vol_occ[2] = {nullptr, nullptr};
@@ -412,8 +413,10 @@ static void ctx_release(DevCtx* c) {
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_cams) cudaFreeHost(c->h_cams);
     if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
+    if (c->vol_surf) cudaDestroySurfaceObject(c->vol_surf);
     if (c->vol_arr) cudaFreeArray(c->vol_arr);
     c->vol_tex = 0;
+    c->vol_surf = 0;
     c->vol_arr = nullptr;
     c->vol_dims[0] = c->vol_dims[1] = c->vol_dims[2] = 0;
     for (int b = 0; b < 2; ++b) {
@@ -580,12 +583,22 @@ static int run_job(Job& J) {
             if (C->vol_dims[0] != vx || C->vol_dims[1] != vy || C->vol_dims[2] != vz) {
                 CUJ(7, cudaStreamSynchronize(stream));
                 if (C->vol_tex) cudaDestroyTextureObject(C->vol_tex);
+                if (C->vol_surf) cudaDestroySurfaceObject(C->vol_surf);
                 if (C->vol_arr) cudaFreeArray(C->vol_arr);
                 C->vol_tex = 0;
+                C->vol_surf = 0;
                 C->vol_arr = nullptr;
                 C->vol_dims[0] = C->vol_dims[1] = C->vol_dims[2] = 0;
                 cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
-                if (cudaMalloc3DArray(&C->vol_arr, &cd, make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz), cudaArrayLayered) == cudaSuccess) {
+                cudaError_t ea = cudaMalloc3DArray(&C->vol_arr, &cd, make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz),
+                                                   cudaArrayLayered | cudaArraySurfaceLoadStore);
+                bool with_surface = ea == cudaSuccess;
+                if (ea != cudaSuccess) {
+                    cudaGetLastError();
+                    C->vol_arr = nullptr;
+                    ea = cudaMalloc3DArray(&C->vol_arr, &cd, make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz), cudaArrayLayered);
+                }
+                if (ea == cudaSuccess) {
                     cudaResourceDesc rd = {};
                     rd.resType = cudaResourceTypeArray;
                     rd.res.array.array = C->vol_arr;
@@ -596,6 +609,10 @@ static int run_job(Job& J) {
                     td.normalizedCoords = 0;
                     if (cudaCreateTextureObject(&C->vol_tex, &rd, &td, nullptr) == cudaSuccess) {
                         C->vol_dims[0] = vx; C->vol_dims[1] = vy; C->vol_dims[2] = vz;
+                        if (with_surface && cudaCreateSurfaceObject(&C->vol_surf, &rd) != cudaSuccess) {
+                            C->vol_surf = 0;
+                            cudaGetLastError();
+                        }
                     } else {
                         cudaFreeArray(C->vol_arr);
                         C->vol_arr = nullptr;
@@ -605,13 +622,9 @@ static int run_job(Job& J) {
                 cudaGetLastError();
             }
             if (C->vol_arr) {
-                cudaMemcpy3DParms cp = {};
-                cp.srcPtr = make_cudaPitchedPtr(ds->d_vox[0], (size_t)vy * sizeof(float), (size_t)vy, (size_t)vx);
-                cp.dstArray = C->vol_arr;
-                cp.extent = make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz);
-                cp.kind = cudaMemcpyDeviceToDevice;
-                CUJ(4, cudaMemcpy3DAsync(&cp, stream));
                 use_tex = true;
+                // empty-space map (and, with a surface, the array fill in the same pass over the volume)
+                bool filled = false;
                 if (!getenv("XRAY_VOLUME_NO_SKIP")) {
                     const size_t nb = volume_brick_count(vx, vy, vz);
                     if (nb > C->vol_occ_cap) {
@@ -624,8 +637,19 @@ static int run_job(Job& J) {
                         if (cudaMalloc(&C->vol_occ[0], nb) == cudaSuccess && cudaMalloc(&C->vol_occ[1], nb) == cudaSuccess) C->vol_occ_cap = nb;
                         cudaGetLastError();
                     }
-                    if (C->vol_occ_cap >= nb)
-                        CUJ(5, build_volume_occupancy((const float*)ds->d_vox[0], vx, vy, vz, C->vol_occ[0], C->vol_occ[1], &vol_occ, stream));
+                    if (C->vol_occ_cap >= nb) {
+                        const unsigned long long surf = getenv("XRAY_VOLUME_MEMCPY3D") ? 0ull : (unsigned long long)C->vol_surf;
+                        CUJ(5, build_volume_occupancy((const float*)ds->d_vox[0], vx, vy, vz, C->vol_occ[0], C->vol_occ[1], &vol_occ, surf, stream));
+                        filled = surf != 0;
+                    }
+                }
+                if (!filled) {
+                    cudaMemcpy3DParms cp = {};
+                    cp.srcPtr = make_cudaPitchedPtr(ds->d_vox[0], (size_t)vy * sizeof(float), (size_t)vy, (size_t)vx);
+                    cp.dstArray = C->vol_arr;
+                    cp.extent = make_cudaExtent((size_t)vy, (size_t)vx, (size_t)vz);
+                    cp.kind = cudaMemcpyDeviceToDevice;
+                    CUJ(4, cudaMemcpy3DAsync(&cp, stream));
                 }
             }
         }

@@ -155,9 +155,12 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_fast_kernel(const
 constexpr int kBrick = 8;
 constexpr int kOccPasses = 8;  // even: the result lands back in the first ping-pong buffer
 
-// one CTA per brick row (fixed brick X, Z): stream the (kBrick+1)^2 voxel rows it touches, coalesced along y
+// one CTA per brick row (fixed brick X, Z): stream the (kBrick+1)^2 voxel rows it touches, coalesced along y.
+// With a surface (surf != 0) the same pass also fills the layered array the render kernel gathers from
+// (rows x in [8X, 8X+8), z in [8Z, 8Z+8) are this CTA's to write; the +1 halo rows are only inspected), which
+// replaces a separate cudaMemcpy3D of the whole volume.
 __global__ void __launch_bounds__(256) brick_occupancy_kernel(const float* __restrict__ vol, int nx, int ny, int nz, int bnx, int bny,
-                                                              unsigned char* __restrict__ occ) {
+                                                              unsigned char* __restrict__ occ, cudaSurfaceObject_t surf) {
     extern __shared__ unsigned int s_flag[];  // one word per 32 voxels along y
     const int bX = blockIdx.x % bnx, bZ = blockIdx.x / bnx;
     const int nwords = (ny + 31) >> 5;
@@ -168,8 +171,11 @@ __global__ void __launch_bounds__(256) brick_occupancy_kernel(const float* __res
     for (int z = z0; z <= z1; ++z)
         for (int x = x0; x <= x1; ++x) {
             const float* __restrict__ row = vol + ((size_t)z * nx + x) * ny;
+            const bool mine = surf != 0 && x < x0 + kBrick && z < z0 + kBrick;
             for (int y = threadIdx.x; y < ny; y += blockDim.x) {
-                const bool nz_ = (__float_as_uint(row[y]) << 1) != 0u;  // anything but +-0 (NaN and Inf included)
+                const float v = row[y];
+                if (mine) surf2DLayeredwrite(v, surf, y * (int)sizeof(float), x, z);
+                const bool nz_ = (__float_as_uint(v) << 1) != 0u;  // anything but +-0 (NaN and Inf included)
                 const unsigned int m = __ballot_sync(__activemask(), nz_);
                 // lanes of a warp cover 32 consecutive y starting at a multiple of 32 (blockDim = 256, y = tid + k*256)
                 if ((threadIdx.x & 31) == 0 && m) atomicOr(&s_flag[y >> 5], m);
@@ -437,11 +443,12 @@ size_t volume_brick_count(int nx, int ny, int nz) {
 }
 
 // Fill occ_a with the empty-space map of d_vol (occ_b is scratch of the same size); returns the buffer holding the result.
+// surf != 0: also copy the volume into the layered array behind that surface (see brick_occupancy_kernel).
 cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
-                                   const unsigned char** result, cudaStream_t stream) {
+                                   const unsigned char** result, unsigned long long surf, cudaStream_t stream) {
     const int bnx = (nx + kBrick - 1) / kBrick, bny = (ny + kBrick - 1) / kBrick, bnz = (nz + kBrick - 1) / kBrick;
     const size_t smem = (size_t)((ny + 31) / 32) * sizeof(unsigned int);
-    brick_occupancy_kernel<<<(unsigned int)(bnx * bnz), 256, smem, stream>>>(d_vol, nx, ny, nz, bnx, bny, occ_a);
+    brick_occupancy_kernel<<<(unsigned int)(bnx * bnz), 256, smem, stream>>>(d_vol, nx, ny, nz, bnx, bny, occ_a, (cudaSurfaceObject_t)surf);
     const size_t n = (size_t)bnx * bny * bnz;
     const unsigned int grid = (unsigned int)((n + 255) / 256);
     unsigned char *src = occ_a, *dst = occ_b;
