@@ -404,6 +404,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_dram_traffic_r1.json")))[args.workload]
         roof["traffic"] = tr["dram_bytes_per_view"] * (views * world * args.steps / max(1.0, launches))
         roof["traffic_source"] = tr["capture"] + " (per view) x views per launch"
+        if clocks and clocks.get("sm_mhz") and tr.get("warp_inst_per_view"):
+            # what actually binds these kernels: warp-instruction issue slots (4 schedulers x 148 SMs x SM clock)
+            inst_s = tr["warp_inst_per_view"] * views * args.steps / secs
+            peak_inst = 4.0 * 148 * clocks["sm_mhz"] * 1e6
+            roof["issue"] = {"warp_inst_per_view": tr["warp_inst_per_view"], "achieved_ginst_per_s": inst_s / 1e9,
+                             "peak_ginst_per_s": peak_inst / 1e9, "frac": inst_s / peak_inst,
+                             "note": "instruction count from the committed ncu capture, time from this run"}
     except (OSError, KeyError, ValueError):
         pass
     if is_volume:
