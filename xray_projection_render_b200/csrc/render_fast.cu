@@ -50,6 +50,49 @@ __device__ __noinline__ float exact_density_cold(const SceneView* sv, const doub
     return rho;
 }
 
+// Cold path of the single-primitive variants (PRIM, n = 1): the same fp64 re-evaluation without the interpreter --
+// position, warp chain, tessellation bounds + fold (objects.go:568-582, :458-464), the one primitive, and the
+// collection rule for one child (objects.go:422-438).  Pointers are the kernel's global-memory arguments, so the
+// loads are plain LDG instead of generic loads through the shared-memory SceneView.  About half the instructions
+// of exact_density_cold, which matters for a gyroid unit cell (one crossing in three lands in the guard band).
+template <int PRIM>
+__device__ __noinline__ float exact_single_cold(const double* __restrict__ f64, const DeformRec* __restrict__ deform, int n_deform,
+                                                const double* ray, const double* __restrict__ s_tab, int base, int nsub, double ds_fine,
+                                                double dm, int tess_f64_idx, int prim_f64_idx, unsigned int cflags) {
+    const int tid = threadIdx.x;
+    const double s = exact_position(s_tab, base, nsub, ds_fine);
+    double x = dadd(ray[0 * kBlockThreads + tid], dmul(ray[3 * kBlockThreads + tid], s));
+    double y = dadd(ray[1 * kBlockThreads + tid], dmul(ray[4 * kBlockThreads + tid], s));
+    double z = dadd(ray[2 * kBlockThreads + tid], dmul(ray[5 * kBlockThreads + tid], s));
+    for (int i = 0; i < n_deform; ++i) Exact::deform(deform[i], x, y, z);
+    SceneView S = {};
+    S.f64 = f64;
+    bool dummy = false;
+    bool inside = true;
+    if (tess_f64_idx >= 0) {
+        Instr I = {};
+        I.f64_idx = (unsigned int)tess_f64_idx;
+        inside = Exact::tess(S, I, x, y, z, dummy);
+    }
+    Instr J = {};
+    J.f64_idx = (unsigned int)prim_f64_idx;
+    double rho = 0.0;
+    bool in;
+    if (PRIM == OP_GYROID) in = Exact::gyroid(S, J, 0, x, y, z, rho, dummy);
+    else if (PRIM == OP_SPHERE) in = Exact::sphere(S, J, 0, x, y, z, rho, dummy);
+    else if (PRIM == OP_BOX) in = Exact::box(S, J, 0, x, y, z, rho, dummy);
+    else in = Exact::cyl(S, J, 0, x, y, z, rho, dummy);
+    double val = (inside && in) ? rho : 0.0;
+    if ((cflags & 0x100u) && !((cflags & F_GREEDY) && val > 0.0)) {  // a collection: sum of one child, clamped to [0,1]
+        if (val < 0.0) val = 0.0;
+        else if (val > 1.0) val = 1.0;
+    }
+    const double r64 = dmul(val, dm);
+    float r = (float)r64;
+    if (r64 != 0.0 && r == 0.0f) r = r64 > 0 ? 1e-30f : -1e-30f;  // keep zero-ness for the transition test
+    return r;
+}
+
 // Cold path for samples within the guard band of a tessellation's outer box or of a unit-cell face: only the
 // period (and the inclusive bounds tests of objects.go:569,459) is in doubt, not the primitives.  Redo position,
 // warp and fold in fp64 exactly as the reference does and hand the folded point back to the fp32 pipeline
@@ -371,6 +414,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
     const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
     const float4* q1 = sF + reinterpret_cast<const uint4*>(sI + rb)[1].x;  // PRIM != 0: the one run's records
     const unsigned int n1 = reinterpret_cast<const uint4*>(sI + rb)[0].y;   //            and its child count
+    const int prim_f64_idx = (int)reinterpret_cast<const uint4*>(sI + rb)[1].y;
     const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
     // cell-list grid sub-arrays (LIST): offsets are in the 5th record word, relative to `grids`
     const uint4 lb = LIST ? *reinterpret_cast<const uint4*>(gF + 4) : make_uint4(0u, 0u, 0u, 0u);
@@ -547,8 +591,14 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         rho *= dmf;
         unc = unc && act;
         if (__any_sync(FULL_MASK, unc)) {
-            const float r = exact_density_cold(&sA->gsv, sRay, P.s_tab, mode == 0 ? k + (INTEG == 1 ? 1 : 0) : kf,
-                                               mode == 0 ? 0 : jf + 1, P.ds_fine, P.dm, unc);
+            float r;
+            if (PRIM != 0 && n1 == 1u)
+                r = exact_single_cold<PRIM>(P.scene.f64, P.scene.deform, n_deform, sRay, P.s_tab, mode == 0 ? k + (INTEG == 1 ? 1 : 0) : kf,
+                                            mode == 0 ? 0 : jf + 1, P.ds_fine, P.dm, SHAPE == SHAPE_TESS ? tess_f64_idx : -1, prim_f64_idx,
+                                            cflags);
+            else
+                r = exact_density_cold(&sA->gsv, sRay, P.s_tab, mode == 0 ? k + (INTEG == 1 ? 1 : 0) : kf, mode == 0 ? 0 : jf + 1,
+                                       P.ds_fine, P.dm, unc);
             if (unc) {
                 rho = r;
                 if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & 4))) ++n_fallback;
