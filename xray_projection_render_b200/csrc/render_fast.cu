@@ -19,8 +19,9 @@
 
 namespace xr {
 
-struct FastArgs {  // uniform per-launch scalars the hot loop needs, staged in shared memory
+struct FastArgs {  // uniform per-launch data the hot loop needs, staged in shared memory
     SceneView gsv;  // global-memory view of the program for the exact path
+    DeformRec d0;   // the first deformation record: one strain field is the common case, read it with LDS broadcasts
 };
 
 // Exact lattice position: coarse sample `base` (nsub = 0), or fine sample j of coarse interval `base`
@@ -361,6 +362,8 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         const uint4* srcF = reinterpret_cast<const uint4*>(P.scene.f32);
         if (!LIST)
             for (int k = tid; k < P.scene.f32_count; k += kBlockThreads) dst[nI + k] = srcF[k];
+        if (P.scene.n_deform > 0 && tid < (int)(sizeof(DeformRec) / sizeof(unsigned int)))
+            reinterpret_cast<unsigned int*>(&sA->d0)[tid] = reinterpret_cast<const unsigned int*>(P.scene.deform)[tid];
         if (tid == 0) {
             SceneView g;
             g.instr = P.scene.instr;
@@ -484,7 +487,11 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         // ---- the single evaluation site ----
         float x = fmaf(pdx, t, pcx), y = fmaf(pdy, t, pcy), z = fmaf(pdz, t, pcz);
         bool unc = false;
-        for (int d = 0; d < n_deform; ++d) Fast::deform(deform[d], x, y, z);
+        if (n_deform != 0) {  // uniform
+            if (n_deform == 1) Fast::deform(sA->d0, x, y, z);  // parameters come from shared memory
+            else
+                for (int d = 0; d < n_deform; ++d) Fast::deform(deform[d], x, y, z);
+        }
         bool alive = act;
         unsigned int um_lo = ~0u, um_hi = ~0u;
         // clearance of this lane, in lattice steps, inside which density() is provably 0 (skipping):
