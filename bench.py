@@ -37,6 +37,8 @@ WORKLOADS = {
     "voxel1024": (None, None, 1440, 2048, "simple", -1.0),                                     # configs[3] (8 GPUs)
     "pillar_array": ("pillar_array.json", None, 2880, 4096, "hierarchical", -1.0),             # configs[4]
     # the reference's two remaining example scenes (not BASELINE configs; regression coverage for sphere / box / pped runs)
+    "lattice_linear": ("lattice.json", "deformation_linear.json", 360, 1024, "hierarchical", -1.0),   # the project's use case: a strained lattice
+    "lattice_sigmoid": ("lattice.json", "deformation_sigmoid.json", 360, 1024, "hierarchical", -1.0),
     "balls": ("balls.json", None, 360, 1024, "hierarchical", -1.0),
     "box_w_pped": ("box_w_pped.json", None, 360, 1024, "hierarchical", -1.0),
 }
