@@ -322,3 +322,63 @@ def test_rays_inside_cell_face_planes(X, O, scenes, name, deform, az):
     refT, _ = osc.render_view(eye, cm, res, FOV, R, ds, "hierarchical")
     assert np.abs(img[0][:, res // 2 - 1:res // 2 + 2].astype(np.float64) - refT[:, res // 2 - 1:res // 2 + 2]).max() <= TOL_FP32
     assert st["fp64_fallbacks"] > 0
+
+
+# ---- one-primitive scenes: the lane-asynchronous kernel (render_fast.cu render_async_kernel) ----
+GYROID_CELL = {"type": "tessellated_obj_coll", "xmin": -0.7, "xmax": 0.7, "ymin": -0.6, "ymax": 0.6, "zmin": -0.65, "zmax": 0.65,
+               "uc": {"xmin": -1.0, "xmax": 1.0, "ymin": -1.0, "ymax": 1.0, "zmin": -1.0, "zmax": 1.0,
+                      "objects": {"objects": [{"type": "gyroid", "center": [0.05, 0.0, -0.02], "scale": 0.12, "thickness": 0.25, "rho": 0.8}]}}}
+
+
+@pytest.mark.parametrize("d", [None] + DEFORMS, ids=lambda d: d["type"] if d else "none")
+def test_gyroid_cell_under_every_warp(X, O, d):
+    """The gyroid skip bound uses the warp's Jacobian and curvature (second-order rule for none / rigid / linear / affine /
+    sigmoid; first-order Lipschitz rule for gaussian and composed chains): each must stay within the tolerances and keep
+    the oracle's sample count."""
+    out, nref, _ = gpu_vs_oracle(X, O, GYROID_CELL, d, res=32, ds=0.002, views=((77.0, 90.0), (205.0, 62.0)))
+    assert_parity(out, nref)
+
+
+@pytest.mark.parametrize("integ", ["hierarchical", "simple"])
+def test_unbounded_gyroid_fine_step(X, O, integ):
+    """A bare gyroid fills the whole integration window: rays end inside a wall, and an in-wall skip must stop at the
+    last lattice sample instead of adding weight for samples the reference never takes."""
+    prim = {"type": "gyroid", "center": [0.0, 0.0, 0.0], "scale": 0.2, "thickness": 0.3, "rho": 0.5}
+    out, nref, _ = gpu_vs_oracle(X, O, prim, res=24, ds=0.001, integ=integ, views=((90.0, 90.0), (10.0, 50.0)))
+    assert_parity(out, nref)
+    coll = {"type": "object_collection", "objects": [dict(prim, rho=1.5)]}  # one child: clamped to 1 unless greedy
+    for greedy in (False, True):
+        out, nref, _ = gpu_vs_oracle(X, O, dict(coll, greedy_dens_eval=greedy), res=24, ds=0.001, integ=integ, views=((120.0, 80.0),))
+        assert_parity(out, nref)
+
+
+def test_async_and_lockstep_kernels_agree(X, scenes):
+    """XRAY_NO_ASYNC routes one-primitive scenes through the warp-synchronous kernel: same images up to fp32 summation
+    order, same reference-equivalent sample counts."""
+    cases = [("pillar_array", None, -1.0, "hierarchical"), ("pillar_array", "deformation_linear", -1.0, "simple"),
+             ("gyroid_example", "deformation_sigmoid", 0.002, "hierarchical"), ("gyroid_example", None, 0.002, "simple")]
+    cams = X.cameras_from_angles([(33.0, 90.0), (140.0, 70.0)], R, FOV)
+    for name, deform, ds, integ in cases:
+        sc = X.Scene(str(scenes / f"{name}.json"), str(scenes / f"{deform}.json") if deform else None)
+        a, sa = X.render_scene(sc, cams, 96, ds=ds, integration=integ, return_stats=True)
+        os.environ["XRAY_NO_ASYNC"] = "1"
+        try:
+            b, sb = X.render_scene(sc, cams, 96, ds=ds, integration=integ, return_stats=True)
+        finally:
+            del os.environ["XRAY_NO_ASYNC"]
+        assert np.abs(a.astype(np.float64) - b).max() <= 2e-6, (name, deform)
+        assert sa["ref_samples"] == sb["ref_samples"]
+
+
+@pytest.mark.parametrize("prim", [
+    {"type": "sphere", "center": [0.2, 0.25, 0.1], "radius": 0.18, "rho": 0.9},
+    {"type": "box", "center": [0.25, 0.2, 0.0], "sides": [0.2, 0.3, 0.8], "rho": 1.0},
+    {"type": "cylinder", "p0": [0.1, 0.1, -0.6], "p1": [0.4, 0.35, 0.6], "radius": 0.07, "rho": 0.7},
+], ids=lambda p: p["type"])
+def test_one_primitive_unit_cells(X, O, prim):
+    """Tessellations of a single sphere / box / (tilted) cylinder: grid-driven empty-space skipping per lane."""
+    obj = {"type": "tessellated_obj_coll", "xmin": -0.9, "xmax": 0.9, "ymin": -0.8, "ymax": 0.8, "zmin": -0.7, "zmax": 0.7,
+           "uc": {"xmin": 0.0, "xmax": 0.5, "ymin": 0.0, "ymax": 0.5, "zmin": -1.0, "zmax": 1.0, "objects": {"objects": [prim]}}}
+    for integ in ("hierarchical", "simple"):
+        out, nref, _ = gpu_vs_oracle(X, O, obj, res=40, ds=0.01, integ=integ)
+        assert_parity(out, nref)

@@ -33,6 +33,8 @@ cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz
 cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
                                const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream);
 size_t fast_kernel_smem_bytes(const RenderParams& P);
+cudaError_t launch_render_async(const RenderParams& P, int shape, int integrator, bool count, int prim, const unsigned char* d_nfine,
+                                int i_coll, int i_tess, cudaStream_t stream);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
                                      int warp_shape, const unsigned char* occ, cudaStream_t stream);
 size_t volume_brick_count(int nx, int ny, int nz);
@@ -657,6 +659,7 @@ static int run_job(Job& J) {
 
     // big collections carry a cell-list grid: their fp32 pool stays in global memory (only instructions are staged)
     bool use_list = false;
+    bool single_async = false;
     int single_prim = 0;  // the op when the (collection of the) scene is exactly one run of cylinders / gyroids / spheres / boxes
     if (shape != 0) {
         const Instr* I = (const Instr*)(J.scene->blob.data() + h->instr_off);
@@ -666,6 +669,8 @@ static int run_job(Job& J) {
         if (!use_list && re - rb == 1 && I[rb].child_bit == 0 && (I[rb].op == OP_CYL || I[rb].op == OP_GYROID || I[rb].op == OP_SPHERE || I[rb].op == OP_BOX) &&
             !getenv("XRAY_NO_SINGLE_PRIM"))
             single_prim = (int)I[rb].op;
+        // exactly one primitive: nothing is shared between the lanes of a warp, so each lane marches on its own
+        single_async = single_prim != 0 && I[rb].n == 1 && !getenv("XRAY_NO_ASYNC");
         if (use_list && J.opts.precision == XRAY_PRECISION_FP32) {
             P.prog_in_smem = 0;
             P.smem_prog_bytes = (unsigned int)((size_t)h->n_instr * sizeof(Instr));
@@ -689,6 +694,8 @@ static int run_job(Job& J) {
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
+        if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && single_async && P.prog_in_smem && fast_kernel_smem_bytes(P) <= 200 * 1024)
+            return launch_render_async(P, shape, J.opts.integration, P.stats != nullptr, single_prim, C->d_nfine, i_coll, i_tess, stream);
         if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && (P.prog_in_smem || use_list) && fast_kernel_smem_bytes(P) <= 200 * 1024)
             return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, use_list, single_prim, C->d_nfine, i_coll, i_tess,
                                       stream);

@@ -12,7 +12,7 @@
 namespace xr {
 
 constexpr uint32_t kMagic = 0x58524159u;  // "XRAY"
-constexpr uint32_t kVersion = 4;
+constexpr uint32_t kVersion = 5;
 constexpr int kMaxVoxelSlots = 4;
 constexpr int kMaxSaveDepth = 6;  // nested save frames (collections/tessellations inside collections)
 constexpr int kFrameWords = 8;    // real-typed words per save frame
@@ -55,13 +55,14 @@ struct Instr {
 //   box      f32: {cx,cy,cz,rho} {hx,hy,hz,tol}                          f64: cx,cy,cz,sx,sy,sz,rho,-
 //   cylinder f32: {p0,rho} {v,inv_vv} {r2,tolr,tolc,-}                   f64: p0(3),p1(3),r,rho
 //   pped     f32: {o,rho} {row0,tol} {row1,-} {row2,-}                   f64: o(3),minv colmajor(9),rho,-
-//   gyroid   f32: {c,rho} {inv_scale,thickness,tol,-}                    f64: c(3),scale,thickness,rho
+//   gyroid   f32: {c,rho} {inv_scale,thickness,tol,m2d} {M2,g1eps,lip,-}     f64: c(3),scale,thickness,rho
+//            (third record: second-order skip bound along the ray, M2 = 0 when the warp chain has no curvature bound)
 //   voxel    f32: {tol,-,-,-}                                            f64: (none)
 //   tess     f32: {oc,tol_o} {oh,-} {ucmin,-} {d,-} {inv_d,tolq}         f64: outer(6: xmin,xmax,..), uc(6)
 //   grid     f32: {gmin,cs_min} {inv_cell,-} {gx,gy,gz (int bits), -} {gx,gy,gz as floats, -}
 //   list grid (F_HAS_LIST) adds a 5th float4 of int bits: u64 offsets (relative to Instr.aux) of
 //            cell_off[ncell+1] (u32), cell_dist[ncell] (u8), idx[] (u16), child_tab[n] (u32 = op<<24 | float4 index)
-constexpr int kF32Sphere = 2, kF32Box = 2, kF32Cyl = 3, kF32Pped = 4, kF32Gyroid = 2, kF32Voxel = 1, kF32Tess = 5,
+constexpr int kF32Sphere = 2, kF32Box = 2, kF32Cyl = 3, kF32Pped = 4, kF32Gyroid = 3, kF32Voxel = 1, kF32Tess = 5,
               kF32Grid = 4;
 constexpr int kF64Sphere = 6, kF64Box = 8, kF64Cyl = 8, kF64Pped = 14, kF64Gyroid = 6, kF64Tess = 12;
 

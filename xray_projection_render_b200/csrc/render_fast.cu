@@ -634,6 +634,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
             if ((um_lo | um_hi) == 0u || !has_grid) {
                 float a = (((um_lo | um_hi) == 0u && rho != 0.0f) || unc) ? 0.0f : clear;
                 if (!act) a = (!hit || k >= k1) ? 1.0e6f : (float)(k0 - k);
+                else a = fminf(a, (float)(k1 - k));  // never run past the lane's last lattice sample (unbounded solids)
                 const int n = __reduce_min_sync(FULL_MASK, (int)fminf(a, 1.0e6f));
                 if (n >= 2) {  // steps k+1 .. k+n-1 are skipped, k+n is evaluated again
                     adv = n;
@@ -663,6 +664,363 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         // the count of fine steps is ray independent given the refined intervals; recount exactly
         add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
     }
+}
+
+
+// =========================================================================================
+// Lane-asynchronous march for scenes that are ONE primitive (a gyroid unit cell, a pillar array):
+// every lane walks its own lattice index, so a lane never waits at another lane's surface crossing.
+// With the warp-synchronous loop above a warp evaluates the UNION of its lanes' critical samples
+// (gyroid + sigmoid config: 340 iterations per warp); here it evaluates the MAXIMUM over lanes
+// (~70, simulation in DESIGN.md section 5).  Nothing is shared between lanes of a one-primitive scene
+// (no candidate masks to merge), so lockstep buys nothing there.  Refinements are not queued: a lane
+// that sees (rho==0) != (prev==0) replays the fine sub-steps of that interval at once, then resumes
+// its coarse walk (same terms as main.go:176-196, summed in a different order; Kahan fp32).
+// =========================================================================================
+
+// Warp stage 0 (the only one these scenes may have for the second-order rule) applied to the sample, plus
+// e = J d, the image of the ray direction under the stage's Jacobian (rigid / linear / affine / sigmoid).
+__device__ __forceinline__ void deform_dir(const DeformRec& r, float& x, float& y, float& z, float dx, float dy, float dz, float& ex,
+                                           float& ey, float& ez) {
+    const float* p = r.f;
+    ex = dx;
+    ey = dy;
+    ez = dz;
+    switch (r.type) {  // uniform
+        case D_AFFINE: {
+            const float nx = p[0] * x + p[1] * y + p[2] * z, ny = p[3] * x + p[4] * y + p[5] * z, nz = p[6] * x + p[7] * y + p[8] * z;
+            ex = p[0] * dx + p[1] * dy + p[2] * dz;
+            ey = p[3] * dx + p[4] * dy + p[5] * dz;
+            ez = p[6] * dx + p[7] * dy + p[8] * dz;
+            x = nx; y = ny; z = nz;
+            break;
+        }
+        case D_LINEAR: {
+            const float nx = x + p[0] * x + p[5] * y + p[4] * z, ny = y + p[5] * x + p[1] * y + p[3] * z,
+                        nz = z + p[4] * x + p[3] * y + p[2] * z;
+            ex = dx + p[0] * dx + p[5] * dy + p[4] * dz;
+            ey = dy + p[5] * dx + p[1] * dy + p[3] * dz;
+            ez = dz + p[4] * dx + p[3] * dy + p[2] * dz;
+            x = nx; y = ny; z = nz;
+            break;
+        }
+        case D_SIGMOID: {
+            float q = r.axis == 0 ? x : (r.axis == 1 ? y : z);
+            const float E = __expf((q - p[1]) * p[2]);  // p[2] = -1/L
+            const float sg = __fdividef(1.0f, 1.0f + E);
+            q += __fdividef(p[0], 1.0f + E);            // same expression as Fast::deform (eps_pos budget)
+            // 1 + (A/L) sigma (1 - sigma); written so that E = inf (sigma = 0) gives 1, not inf * 0
+            const float jac = fmaf(-p[0] * p[2], sg * (1.0f - sg), 1.0f);
+            if (r.axis == 0) { x = q; ex = dx * jac; }
+            else if (r.axis == 1) { y = q; ey = dy * jac; }
+            else { z = q; ez = dz * jac; }
+            break;
+        }
+        default: Fast::deform(r, x, y, z); break;  // rigid: e = d; anything else never uses e (M2 = 0)
+    }
+}
+
+// Gyroid test with the second-order skip bound: the largest delta (distance along the ray) with
+// G1 delta + M2 delta^2 / 2 <= m, G1 >= |h'(t)| from the local gradient, m = distance of |g| - thickness from the
+// guard band.  Inside [t, t + delta] the exact classification cannot change.  margin is returned in the units the
+// march converts with skip_m2s (object-space max-norm distance = delta * Lipschitz factor).
+__device__ __forceinline__ void prim_gyroid_so(const float4* __restrict__ q, float x, float y, float z, float ex, float ey, float ez,
+                                               bool& in, bool& near, float& rho, float& margin) {
+    const float4 a = q[0], b = q[1], c = q[2];
+    float sx, cx, sy, cy, sz, cz;
+    fast_sincos((x - a.x) * b.x, &sx, &cx);
+    fast_sincos((y - a.y) * b.x, &sy, &cy);
+    fast_sincos((z - a.z) * b.x, &sz, &cz);
+    const float t = fabsf(sx * cy + sy * cz + sz * cx) - b.y;
+    in = t < 0.0f;
+    near = fabsf(t) < b.z;
+    rho = a.w;
+    const float m = fmaxf(fabsf(t) - b.z, 0.0f);
+    if (c.x > 0.0f) {  // uniform
+        const float gx = cx * cy - sz * sx, gy = cy * cz - sx * sy, gz = cz * cx - sy * sz;
+        const float G1 = (fabsf(gx * ex + gy * ey + gz * ez) + c.y) * fabsf(b.x);
+        const float delta = __fdividef(2.0f * m, G1 + sqrtf(fmaf(2.0f * c.x, m, G1 * G1)));
+        margin = delta * c.z;
+    } else {
+        margin = m * b.w;
+    }
+}
+
+template <int SHAPE, int INTEG, bool COUNT, int PRIM>
+#ifndef XR_ASYNC_MINBLOCKS
+#define XR_ASYNC_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_async_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
+                                                                         int i_coll, int i_tess) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles]
+    const Instr* sI = reinterpret_cast<const Instr*>(smem);
+    const float4* sF = reinterpret_cast<const float4*>(smem + (size_t)P.scene.n_instr * sizeof(Instr));
+    FastArgs* sA = reinterpret_cast<FastArgs*>(smem + P.smem_prog_bytes);
+    double* sRay = reinterpret_cast<double*>(sA + 1);
+    const int tid = threadIdx.x;
+    {
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        const uint4* srcI = reinterpret_cast<const uint4*>(P.scene.instr);
+        const int nI = P.scene.n_instr * 2;
+        for (int k = tid; k < nI; k += kBlockThreads) dst[k] = srcI[k];
+        const uint4* srcF = reinterpret_cast<const uint4*>(P.scene.f32);
+        for (int k = tid; k < P.scene.f32_count; k += kBlockThreads) dst[nI + k] = srcF[k];
+        if (P.scene.n_deform > 0 && tid < (int)(sizeof(DeformRec) / sizeof(unsigned int)))
+            reinterpret_cast<unsigned int*>(&sA->d0)[tid] = reinterpret_cast<const unsigned int*>(P.scene.deform)[tid];
+        if (tid == 0) {
+            SceneView g;
+            g.instr = P.scene.instr;
+            g.f32 = P.scene.f32;
+            g.f64 = P.scene.f64;
+            g.grids = P.scene.grids;
+            g.deform = P.scene.deform;
+            g.n_instr = P.scene.n_instr;
+            g.n_deform = P.scene.n_deform;
+            g.vox = P.scene.vox;
+            sA->gsv = g;
+        }
+    }
+
+    int view, i, j;
+    pixel_of_thread(P, view, i, j);
+    const bool valid = i < P.res && j < P.res;
+    if (!valid) { i = 0; j = 0; }
+    int k, k1;
+    float pcx, pcy, pcz, pdx, pdy, pdz;
+    {
+        const Ray64 ray = make_ray(P.cams[view], i, j, P.res);
+        double s_in, s_out;
+        const bool hit = valid && clip_ray(ray, P.aabb_lo, P.aabb_hi, s_in, s_out);
+        step_range(P, hit, s_in, s_out, INTEG == 1 ? 1 : 0, k, k1);  // !hit: k = k1 = 0, the lane never becomes active
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            sRay[a * kBlockThreads + tid] = ray.o[a];
+            sRay[(3 + a) * kBlockThreads + tid] = ray.d[a];
+        }
+        pcx = (float)(ray.o[0] + ray.d[0] * P.s_center);
+        pcy = (float)(ray.o[1] + ray.d[1] * P.s_center);
+        pcz = (float)(ray.o[2] + ray.d[2] * P.s_center);
+        pdx = (float)ray.d[0];
+        pdy = (float)ray.d[1];
+        pdz = (float)ray.d[2];
+    }
+    __syncthreads();
+
+    // shape constants (uniform)
+    const uint4 cw0 = reinterpret_cast<const uint4*>(sI + i_coll)[0];
+    const uint4 cw1 = reinterpret_cast<const uint4*>(sI + i_coll)[1];
+    const bool is_coll = cw0.x == OP_COLL_BEGIN;
+    const int rb = is_coll ? i_coll + 1 : i_coll;
+    const unsigned int cflags = is_coll ? (cw0.z | 0x100u) : 0u;
+    const bool has_grid = is_coll && (cw0.z & F_HAS_GRID);
+    const float4* gF = sF + cw1.x;  // grid record (valid when has_grid)
+    const float4* q1 = sF + reinterpret_cast<const uint4*>(sI + rb)[1].x;  // the primitive's records
+    const int prim_f64_idx = (int)reinterpret_cast<const uint4*>(sI + rb)[1].y;
+    const unsigned long long* __restrict__ grids = P.scene.grids + cw1.w;
+    const float4* tF = sF + (SHAPE == SHAPE_TESS ? reinterpret_cast<const uint4*>(sI + i_tess)[1].x : 0u);
+    const int tess_f64_idx = SHAPE == SHAPE_TESS ? (int)reinterpret_cast<const uint4*>(sI + i_tess)[1].y : 0;
+    const int n_deform = P.scene.n_deform;
+    const DeformRec* __restrict__ deform = P.scene.deform;
+    const bool clamps = (cflags & 0x100u) != 0u;  // a collection clamps its sum (objects.go:431-436) ...
+    const bool greedy = (cflags & F_GREEDY) != 0u;  // ... unless greedy returned the first positive child (:425-427)
+
+    const float dmf = P.dm_f, dsf = P.ds_fine_f, wC = P.ds_f, wF = P.ds_fine_f;
+    float accT = 0.0f, cmpT = 0.0f;
+    float prev = 0.0f;
+    int jf = 0, nf = 0, kf = 0;  // fine replay of interval kf: sub-step jf of nf
+    unsigned int n_eval = 0, n_fine = 0, n_fallback = 0, prim_tests = 0;
+
+    while (__any_sync(FULL_MASK, jf < nf || k < k1)) {
+        const bool fine = jf < nf;
+        const bool act = fine || k < k1;
+        const int base = act ? (fine ? kf : k + (INTEG == 1 ? 1 : 0)) : 0;
+        const int nsub = fine ? jf + 1 : 0;
+        float t = __ldg(P.t_tab + base);
+        if (fine) t = fmaf((float)nsub, dsf, t);
+
+        // ---- the evaluation site (same arithmetic as the warp-synchronous kernel) ----
+        float x = fmaf(pdx, t, pcx), y = fmaf(pdy, t, pcy), z = fmaf(pdz, t, pcz);
+        float ex = pdx, ey = pdy, ez = pdz;
+        if (n_deform != 0) {  // uniform
+            if (n_deform == 1) deform_dir(sA->d0, x, y, z, pdx, pdy, pdz, ex, ey, ez);
+            else
+                for (int d = 0; d < n_deform; ++d) Fast::deform(deform[d], x, y, z);
+        }
+        bool alive = act;
+        bool occupied = true;   // the lane's grid cell lists the primitive (always true without a grid)
+        float clear = 0.0f;     // lattice steps inside which density() provably keeps this sample's value
+        float tess_limit = 3.0e38f;
+        if (SHAPE == SHAPE_TESS) {
+            const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
+            const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
+            const float qx = (x - um.x) * id.x, qy = (y - um.y) * id.y, qz = (z - um.z) * id.z;
+            const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+            float rx = qx - fx, ry = qy - fy, rz = qz - fz;
+            const float lo = fminf(rx, fminf(ry, rz)), hi = fmaxf(rx, fmaxf(ry, rz));
+            bool inside = m <= 0.0f;  // outer bounds inclusive (objects.go:569)
+            const bool edge = alive && ((fabsf(m) < oc.w) || (inside && (lo < id.w || hi > 1.0f - id.w)));
+            x = fmaf(-dd.x, fx, x);
+            y = fmaf(-dd.y, fy, y);
+            z = fmaf(-dd.z, fz, z);
+            if (__any_sync(FULL_MASK, edge)) {  // period / bounds in doubt: exact fold, then carry on in fp32
+                const float4 e = exact_fold_cold(&sA->gsv, sRay, P.s_tab, base, nsub, P.ds_fine, tess_f64_idx);
+                if (edge) {
+                    x = e.x;
+                    y = e.y;
+                    z = e.z;
+                    inside = e.w != 0.0f;
+                    rx = (x - um.x) * id.x;
+                    ry = (y - um.y) * id.y;
+                    rz = (z - um.z) * id.z;
+                    if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & (fabsf(m) < oc.w ? 1 : 2)))) ++n_fallback;
+                }
+            }
+            alive = alive && inside;
+            if (has_grid) {  // the grid spans exactly the unit cell: cell = floor(fraction * g), fraction in [0,1]
+                const float4 gd = gF[2], gf = gF[3];
+                const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
+                const int ix = min(gx - 1, (int)(rx * gf.x));
+                const int iy = min(gy - 1, (int)(ry * gf.y));
+                const int iz = min(gz - 1, (int)(rz * gf.z));
+                const unsigned int cell = (unsigned int)((iz * gy + iy) * gx + ix);
+                uint2 mk = make_uint2(0u, 0u);
+                if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + cell);
+                if (mk.y >> 31) {  // empty cell: low byte = Chebyshev distance (cells) to the nearest occupied cell
+                    clear = (float)((mk.x & 255u) - 1u) * (gF[0].w * P.skip_m2s);
+                    mk = make_uint2(0u, 0u);
+                }
+                occupied = (mk.x | mk.y) != 0u;
+            }
+            // outside the outer box (Chebyshev distance m > 0) nothing can be hit for m / (ds * lip) steps
+            if (act && !inside) clear = fmaxf(m - 4.0f * oc.w, 0.0f) * P.skip_m2s;
+            // a skip justified by the primitive's own margin must stay inside this period and inside the outer box
+            if (!has_grid)
+                tess_limit = fminf(fminf(fminf(rx, 1.0f - rx) * fabsf(dd.x), fminf(ry, 1.0f - ry) * fabsf(dd.y)),
+                                   fminf(fminf(rz, 1.0f - rz) * fabsf(dd.z), -m));
+        } else if (has_grid) {
+            const float4 g0 = gF[0], g1 = gF[1], gd = gF[2];
+            const int gx = __float_as_int(gd.x), gy = __float_as_int(gd.y), gz = __float_as_int(gd.z);
+            const int ix = min(gx - 1, max(0, __float2int_rd((x - g0.x) * g1.x)));
+            const int iy = min(gy - 1, max(0, __float2int_rd((y - g0.y) * g1.y)));
+            const int iz = min(gz - 1, max(0, __float2int_rd((z - g0.z) * g1.z)));
+            const unsigned int cell = (unsigned int)((iz * gy + iy) * gx + ix);
+            uint2 mk = make_uint2(0u, 0u);
+            if (alive) mk = __ldg(reinterpret_cast<const uint2*>(grids) + cell);
+            if (mk.y >> 31) {
+                clear = (float)((mk.x & 255u) - 1u) * (g0.w * P.skip_m2s);
+                mk = make_uint2(0u, 0u);
+            }
+            occupied = (mk.x | mk.y) != 0u;
+        }
+        const bool test = alive && occupied;
+        float rho = 0.0f;
+        bool unc = false;
+        if (__any_sync(FULL_MASK, test)) {
+            bool in, near;
+            float pr, clr = 0.0f;
+            if (PRIM == OP_GYROID) prim_gyroid_so(q1, x, y, z, ex, ey, ez, in, near, pr, clr);
+            else if (PRIM == OP_SPHERE) prim_sphere(q1, x, y, z, in, near, pr);
+            else if (PRIM == OP_BOX) prim_box(q1, x, y, z, in, near, pr);
+            else prim_cyl(q1, x, y, z, in, near, pr);
+            if (COUNT) prim_tests += test ? 1u : 0u;
+            unc = near && test;
+            rho = (in && test) ? pr : 0.0f;
+            if (clamps && !(greedy && pr > 0.0f)) rho = __saturatef(rho);
+            if (!has_grid && test) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
+        }
+        rho *= dmf;
+        if (__any_sync(FULL_MASK, unc)) {
+            const float r = exact_single_cold<PRIM>(P.scene.f64, P.scene.deform, n_deform, sRay, P.s_tab, base, nsub, P.ds_fine, P.dm,
+                                                    SHAPE == SHAPE_TESS ? tess_f64_idx : -1, prim_f64_idx, cflags);
+            if (unc) {
+                rho = r;
+                if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & 4))) ++n_fallback;
+            }
+        }
+
+        // ---- per-lane bookkeeping ----
+        if (fine) {
+            XR_KADD(rho * wF);
+            ++jf;
+            if (COUNT) {
+                ++n_eval;
+                ++n_fine;
+            }
+        } else if (act) {
+            if (COUNT) ++n_eval;
+            float w = wC;
+            if (INTEG == 1 && ((rho == 0.0f) != (prev == 0.0f))) {  // main.go:181: refine (left, right], right = this sample
+                kf = k;
+                nf = nfine_tab[k];
+                jf = 0;
+                w = wF;  // T += rho*ds (main.go:188) instead of rho*DS (main.go:190)
+            }
+            XR_KADD(rho * w);
+            prev = rho;
+            // Exact skipping, per lane: the next n - 1 lattice samples provably return this sample's rho (empty grid
+            // cells with clearance, outside the outer box, or the primitive's own margin), so they add
+            // (n-1)*rho*DS and flip nothing.
+            int adv = 1;
+            if (!occupied || !has_grid) {
+                float a = ((!occupied && rho != 0.0f) || unc) ? 0.0f : clear;
+                a = fminf(a, (float)(k1 - k));  // never past the lane's last lattice sample
+                const int n = (int)a;
+                if (n >= 2) {
+                    adv = n;
+                    if (rho != 0.0f) XR_KADD(rho * wC * (float)(n - 1));
+                }
+            }
+            k += adv;
+        }
+    }
+    const double T = P.flat_field + ((double)accT - (double)cmpT);
+    store_pixel(P, view, i, j, valid, exp(-T));
+    if (COUNT) add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
+}
+
+size_t async_kernel_smem_bytes(const RenderParams& P) { return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double); }
+
+template <int SHAPE, int INTEG, bool COUNT, int PRIM>
+static cudaError_t launch_async_one(const RenderParams& P, const unsigned char* nfine, int i_coll, int i_tess, unsigned int grid,
+                                    cudaStream_t stream) {
+    auto kern = render_async_kernel<SHAPE, INTEG, COUNT, PRIM>;
+    const size_t smem = async_kernel_smem_bytes(P);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kBlockThreads, smem, stream>>>(P, nfine, i_coll, i_tess);
+    return cudaGetLastError();
+}
+
+// One-primitive scenes (prim = OP_CYL / OP_GYROID / OP_SPHERE / OP_BOX, run length 1, no cell-list grid).
+cudaError_t launch_render_async(const RenderParams& P, int shape, int integrator, bool count, int prim, const unsigned char* d_nfine,
+                                int i_coll, int i_tess, cudaStream_t stream) {
+    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    if (grid == 0) return cudaSuccess;
+#define XR_AGO(S, I, C, Q) return launch_async_one<S, I, C, Q>(P, d_nfine, i_coll, i_tess, grid, stream)
+#define XR_APRIM(S, I, C)                                          \
+    do {                                                           \
+        if (prim == (int)OP_CYL) XR_AGO(S, I, C, (int)OP_CYL);     \
+        if (prim == (int)OP_GYROID) XR_AGO(S, I, C, (int)OP_GYROID); \
+        if (prim == (int)OP_SPHERE) XR_AGO(S, I, C, (int)OP_SPHERE); \
+        if (prim == (int)OP_BOX) XR_AGO(S, I, C, (int)OP_BOX);     \
+    } while (0)
+#define XR_ACOUNT(S, I)                  \
+    do {                                 \
+        if (count) XR_APRIM(S, I, true); \
+        else XR_APRIM(S, I, false);      \
+    } while (0)
+    if (shape == SHAPE_FLAT) {
+        if (integrator == 0) XR_ACOUNT(SHAPE_FLAT, 0);
+        else XR_ACOUNT(SHAPE_FLAT, 1);
+    } else {
+        if (integrator == 0) XR_ACOUNT(SHAPE_TESS, 0);
+        else XR_ACOUNT(SHAPE_TESS, 1);
+    }
+#undef XR_ACOUNT
+#undef XR_APRIM
+#undef XR_AGO
+    return cudaErrorInvalidValue;
 }
 
 size_t fast_kernel_smem_bytes(const RenderParams& P) {

@@ -778,6 +778,39 @@ static double deform_eps_pos(const std::vector<Deform>& ds, double* lip_out = nu
     return ep;
 }
 
+// Second-order data of the warp chain W for the gyroid skip bound (render_fast.cu prim_gyroid_so): an upper
+// bound jac2 of the Jacobian's 2-norm and curv of |D^2 W[d,d]| for unit d.  Returns false when the chain
+// has no such bound here (gaussian bumps, composed chains): those keep the first-order Lipschitz rule.
+static bool deform_second_order(const std::vector<Deform>& ds, double* jac2, double* curv) {
+    *jac2 = 1.0;
+    *curv = 0.0;
+    if (ds.empty()) return true;
+    if (ds.size() != 1) return false;
+    const Deform& d = ds[0];
+    switch (d.type) {
+        case D_RIGID: return true;
+        case D_SIGMOID:
+            if (!(std::fabs(d.d[2]) > 0.0)) return false;
+            *jac2 = 1.0 + std::fabs(d.d[0] / (4.0 * d.d[2]));          // sigma' <= 1/4
+            *curv = std::fabs(d.d[0]) * 0.0962251 / (d.d[2] * d.d[2]);  // |sigma''| <= 1/(6 sqrt 3)
+            return true;
+        case D_AFFINE:
+        case D_LINEAR: {
+            double fro = 0.0;
+            if (d.type == D_AFFINE) {
+                for (int i = 0; i < 9; ++i) fro += d.d[i] * d.d[i];
+            } else {
+                const double* e = d.d;
+                const double L[9] = {1 + e[0], e[5], e[4], e[5], 1 + e[1], e[3], e[4], e[3], 1 + e[2]};
+                for (int i = 0; i < 9; ++i) fro += L[i] * L[i];
+            }
+            *jac2 = std::sqrt(fro);  // Frobenius >= 2-norm
+            return std::isfinite(*jac2);
+        }
+        default: return false;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Flattening
 // ---------------------------------------------------------------------------------------
@@ -788,6 +821,9 @@ struct Builder {
     std::vector<uint64_t> grids;
     int save_depth = 0, save_depth_max = 0;
     double ep = kEpsPosBase;
+    double warp_lip = 1.0;                    // inf-norm Lipschitz factor of the warp chain (deform_eps_pos)
+    bool so_ok = false;                       // deform_second_order
+    double so_jac2 = 1.0, so_curv = 0.0;
     const XRayScene* sc = nullptr;
     std::string err;
 
@@ -885,6 +921,15 @@ static void emit_prim_params(Builder& B, const Node& n) {
             B.f4(p[0], p[1], p[2], p[5]);
             // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
             B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
+            // Along a ray, h(t) = g(q(t)), q = (W(o + d t) - c)/scale:  |h''| <= 2 |q'|^2 + |grad g . q''|
+            // (each term sin a cos b has a Hessian of 2-norm <= 1 on its coordinate pair and every coordinate
+            // sits in two terms; |dg/dq_i| <= 2).  So |h(t + tau) - h(t)| <= |h'(t)| tau + M2 tau^2 / 2.
+            {
+                const double as = std::fabs(scale);
+                const double M2 = B.so_ok ? 1.01 * (2.0 * (B.so_jac2 / as) * (B.so_jac2 / as) + 3.0 * B.so_curv / as) : 0.0;
+                // g1eps: absolute slack added to |grad g . J d| (fp32 evaluation of gradient and Jacobian)
+                B.f4(std::isfinite(M2) ? up32(M2) : 0.0, up32(1e-3 * B.so_jac2), up32(std::fmax(1.0, B.warp_lip)), 0);
+            }
             B.d64(p, 6, kF64Gyroid);
             break;
         }
@@ -1362,6 +1407,8 @@ static bool build_blob(XRayScene& sc, std::string& err) {
     B.sc = &sc;
     double warp_lip = 1.0;
     B.ep = deform_eps_pos(sc.deforms, &warp_lip);
+    B.warp_lip = warp_lip;
+    B.so_ok = deform_second_order(sc.deforms, &B.so_jac2, &B.so_curv);
     if (!emit_node(B, sc.root, true, 0)) {
         err = B.err;
         return false;
