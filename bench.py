@@ -75,7 +75,34 @@ def scene_flops_model(obj: dict, deform: dict | None):
             prim.append(FLOPS_PRIM[t] + 1)
 
     walk(obj)
-    return per_sample, (sum(prim) / len(prim) if prim else 0.0)
+    return per_sample, (sum(prim) / len(prim) if prim else 0.0), float(sum(prim))
+
+
+def inbounds_samples(cams, res, lo, hi, ds, sub=128):
+    """Reference-equivalent coarse samples that fall inside the scene's bounding box (where the Go path does its
+    arithmetic: everything outside returns from a bounds test), summed over the views: slab clipping of every ray of a
+    sub x sub pixel subsample, scaled to res x res.  Used only for the SURVEY 8(d) brute-force flop figure."""
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    if not (np.isfinite(lo).all() and np.isfinite(hi).all()):
+        lo, hi = np.maximum(lo, -1.74), np.minimum(hi, 1.74)
+    sub = min(sub, res)
+    px = (np.arange(sub) * (res // sub)) / (res / 2.0) - 1.0
+    gi, gj = np.meshgrid(px, px, indexing="ij")
+    total = 0.0
+    for c in cams:
+        eye = np.array(list(c.eye))
+        m = np.array(list(c.view)).reshape(4, 4)
+        f = 1.0 / np.tan(np.radians(c.fov_y) / 2.0)
+        v = np.stack([gi, gj, np.full_like(gi, -f), np.ones_like(gi)], -1) @ m.T
+        d = v[..., :3] / v[..., 3:4] - eye
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a0, a1 = (lo - eye) / d, (hi - eye) / d
+        t0 = np.nanmax(np.minimum(a0, a1), axis=-1)
+        t1 = np.nanmin(np.maximum(a0, a1), axis=-1)
+        t0, t1 = np.maximum(t0, c.R - 1.74), np.minimum(t1, c.R + 1.74)
+        total += float(np.maximum(t1 - t0, 0.0).sum()) / ds
+    return total * (res / sub) ** 2
 
 
 class ClockSampler:
@@ -315,13 +342,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         def step_e2e():
             X.render_volume(vol_np, cams, res, ds=ds_v, out=out_host.numpy())
 
-        per_sample, per_prim = 3 + 6, 14 + 2
+        per_sample, per_prim, brute_prims = 3 + 6, 14 + 2, 0.0
         scene = None
         h2d_step = vol_dev.numel() * 4
     else:
         scene = X.Scene(str(SCENES / obj), str(SCENES / deform) if deform else None)
         ds_v = scene.auto_ds() if ds <= 0 else ds
-        per_sample, per_prim = scene_flops_model(scene.object_map, scene.deformation_map)
+        per_sample, per_prim, brute_prims = scene_flops_model(scene.object_map, scene.deformation_map)
 
         def step_device(st=None):
             X.render_scene_device(scene, cams, res, out_dev, integration=integ, precision="fp32", ds=ds_v,
@@ -402,6 +429,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "algorithmic_flops_per_launch": alg_flops / max(1.0, launches), "avg_launch_ms": kernel_ms,
             "flops_model": {"per_evaluated_sample": per_sample, "per_primitive_test": per_prim},
             "evaluated_samples": evaluated, "primitive_tests": prim_tests, "fp64_fallbacks": fallbacks}
+    if not is_volume:
+        # SURVEY.md 8(d) as written: algorithmic flops of the reference's own algorithm (every child of the collection
+        # tested at every sample inside the scene bounds, nothing outside) for the samples this run covered.  The kernel
+        # does not execute these flops -- culling and exact skipping remove most of them -- so this "fraction" states how
+        # far the run is ahead of an fp32 brute-force evaluator running AT the FP32 roofline, and may exceed 1.
+        lo, hi = scene.bounds()
+        inb = inbounds_samples(cams, res, lo, hi, ds_v) * args.steps  # this rank; ranks are symmetric under weak scaling
+        brute = per_sample + brute_prims
+        roof["survey_8d_brute_force"] = {
+            "flops_per_inbounds_sample": brute, "inbounds_samples": inb * world,
+            "achieved": inb * brute / secs / 1e12, "unit": "TFLOP/s (reference-algorithm flops / GPU)",
+            "frac": inb * brute / secs / 1e12 / peak_tflops if peak_tflops else None,
+            "note": "flops the reference's brute-force density() spends on these samples, not flops executed here"}
     try:  # DRAM traffic of this kernel per launch, from the committed ncu capture of the same workload
         tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_dram_traffic_r1.json")))[args.workload]
         roof["traffic"] = tr["dram_bytes_per_view"] * (views * world * args.steps / max(1.0, launches))

@@ -60,3 +60,17 @@ def O():
 @pytest.fixture(scope="session")
 def scenes():
     return SCENES
+
+
+@pytest.fixture(scope="session")
+def host_replay(X, tmp_path_factory):
+    """tests/c/host_loader_replay.c built with gcc: the Go host's dlopen/dlsym/call sequence from plain C."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = tmp_path_factory.mktemp("replay") / "host_loader_replay"
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "tests" / "c" / "host_loader_replay.c"),
+                           "-o", str(exe), "-ldl", "-lm"])
+    return str(exe)

@@ -275,3 +275,14 @@ def test_empty_space_skipping_is_exact(X, O, monkeypatch):
     assert st["ref_samples"] == st0["ref_samples"]
     assert st["evaluated_samples"] < 0.6 * st0["evaluated_samples"]  # most of the volume really is skipped
     assert img.min() < 0.95
+
+
+def test_go_host_probe_from_c(X, host_replay):
+    """cuda_test.go:15-28 probeCUDA (1x1x1 volume, identity view, one pixel) and the voxeliser calls of cuda_voxel.go:42-50,
+    made from a plain C program through dlopen/dlsym exactly as the Go host's cgo preamble does."""
+    import subprocess
+    from pathlib import Path
+
+    lib = str(Path(X.__file__).resolve().parent / "lib" / "libcuda_render.so")
+    r = subprocess.run([host_replay, lib, "probe"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok probe", r.stderr

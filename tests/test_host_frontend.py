@@ -29,6 +29,24 @@ def test_library_exports_every_declared_symbol(X):
     assert set(X._lib.LEGACY_SYMBOLS) <= names and set(X._lib.EXTENDED_SYMBOLS) <= names
 
 
+def test_go_host_load_sequence_from_c(X, host_replay, monkeypatch):
+    """cuda_backend.go:27-43,103-114 replayed by a C program that includes only include/xray_cuda_render.h:
+    dlopen(RTLD_LAZY|RTLD_LOCAL) of the path in XRAY_CUDA_LIB, the three legacy symbols (all required), struct sizes,
+    and non-zero returns (never a crash or exit) for bad arguments.  No compute call: runs without a GPU."""
+    import subprocess
+
+    lib = str(ROOT / "xray_projection_render_b200" / "lib" / "libcuda_render.so")
+    r = subprocess.run([host_replay, lib, "symbols"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    monkeypatch.setenv("XRAY_CUDA_LIB", lib)
+    r = subprocess.run([host_replay, "-", "symbols"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok symbols", r.stderr
+    r = subprocess.run([host_replay, "/nonexistent/libcuda_render.so", "symbols"], capture_output=True, text=True)
+    assert r.returncode == 1  # the loader's -1: dlopen failed
+    r = subprocess.run([host_replay, str(ROOT / "oracle" / "libxray_oracle.so"), "symbols"], capture_output=True, text=True)
+    assert r.returncode == 2  # a library without the three symbols is refused (-2), as the Go loader does
+
+
 def test_legacy_struct_layouts(X):
     # SURVEY.md 8b [probe]: CylinderParams 32 B, XRayCameraParams 84 B (view@12, fov_y@76, R@80), align 4
     C, P = X._lib.CylinderParams, X._lib.XRayCameraParams

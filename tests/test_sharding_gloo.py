@@ -100,9 +100,9 @@ def test_bench_workloads_cover_baseline_configs():
     assert w["gyroid_sigmoid"][:5] == ("gyroid_example.json", "deformation_sigmoid.json", 720, 1024, "hierarchical")
     assert w["voxel1024"][2:5] == (1440, 2048, "simple")
     assert w["pillar_array"][2:5] == (2880, 4096, "hierarchical")
-    per_sample, per_prim = bench.scene_flops_model({"type": "object_collection", "objects": [
+    per_sample, per_prim, brute = bench.scene_flops_model({"type": "object_collection", "objects": [
         {"type": "sphere"}, {"type": "cylinder"}]}, None)
-    assert per_sample == 6 + 2 and per_prim == ((9 + 1) + (27 + 1)) / 2
+    assert per_sample == 6 + 2 and per_prim == ((9 + 1) + (27 + 1)) / 2 and brute == (9 + 1) + (27 + 1)
 
 
 def test_synthetic_volume_definition():

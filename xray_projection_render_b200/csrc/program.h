@@ -12,7 +12,7 @@
 namespace xr {
 
 constexpr uint32_t kMagic = 0x58524159u;  // "XRAY"
-constexpr uint32_t kVersion = 5;
+constexpr uint32_t kVersion = 6;
 constexpr int kMaxVoxelSlots = 4;
 constexpr int kMaxSaveDepth = 6;  // nested save frames (collections/tessellations inside collections)
 constexpr int kFrameWords = 8;    // real-typed words per save frame
@@ -53,7 +53,7 @@ struct Instr {
 // fp32 pool record sizes in float4 units, fp64 pool record sizes in doubles.
 //   sphere   f32: {cx,cy,cz,rho} {r2,tol,-,-}                            f64: cx,cy,cz,r,rho,-
 //   box      f32: {cx,cy,cz,rho} {hx,hy,hz,tol}                          f64: cx,cy,cz,sx,sy,sz,rho,-
-//   cylinder f32: {p0,rho} {v,inv_vv} {r2,tolr,tolc,-}                   f64: p0(3),p1(3),r,rho
+//   cylinder f32: {p0,rho} {v,inv_vv} {r2,tolr,tolc,tolc/tolr}            f64: p0(3),p1(3),r,rho
 //   pped     f32: {o,rho} {row0,tol} {row1,-} {row2,-}                   f64: o(3),minv colmajor(9),rho,-
 //   gyroid   f32: {c,rho} {inv_scale,thickness,tol,m2d} {M2,g1eps,lip,-}     f64: c(3),scale,thickness,rho
 //            (third record: second-order skip bound along the ray, M2 = 0 when the warp chain has no curvature bound)

@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
         bool alive = act;
         bool occupied = true;   // the lane's grid cell lists the primitive (always true without a grid)
         float clear = 0.0f;     // lattice steps inside which density() provably keeps this sample's value
-        float tess_limit = 3.0e38f;
+        float tess_limit = 3.0e38f;  // object-space distance to the nearest unit-cell face / outer-box exit
         if (SHAPE == SHAPE_TESS) {
             const float4 oc = tF[0], oh = tF[1], um = tF[2], dd = tF[3], id = tF[4];
             const float m = fmaxf(fabsf(x - oc.x) - oh.x, fmaxf(fabsf(y - oc.y) - oh.y, fabsf(z - oc.z) - oh.z));
@@ -927,9 +927,15 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
             unc = near && test;
             rho = (in && test) ? pr : 0.0f;
             if (clamps && !(greedy && pr > 0.0f)) rho = __saturatef(rho);
+            // the gyroid's own clearance, never across a unit-cell face or out of the outer box.  (Distance-to-surface
+            // clearances for spheres / boxes / cylinders were measured and rejected: on the pillar array they remove 3 % of
+            // the evaluations and cost 30 % in extra arithmetic per sample; grid scenes skip through empty cells only.)
             if (!has_grid && test) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
         }
         rho *= dmf;
+        // Guard-band samples: the fp64 reference decides, at once.  (Parking such lanes until several of a warp wait and
+        // serving them with one call was measured: 4x fewer calls, but the parked lanes stretch the warp's critical path --
+        // gyroid +1 %, pillar array -24 % at a threshold of 4 lanes.)
         if (__any_sync(FULL_MASK, unc)) {
             const float r = exact_single_cold<PRIM>(P.scene.f64, P.scene.deform, n_deform, sRay, P.s_tab, base, nsub, P.ds_fine, P.dm,
                                                     SHAPE == SHAPE_TESS ? tess_f64_idx : -1, prim_f64_idx, cflags);
@@ -963,7 +969,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
             // (n-1)*rho*DS and flip nothing.
             int adv = 1;
             if (!occupied || !has_grid) {
-                float a = ((!occupied && rho != 0.0f) || unc) ? 0.0f : clear;
+                float a = unc ? 0.0f : clear;
                 a = fminf(a, (float)(k1 - k));  // never past the lane's last lattice sample
                 const int n = (int)a;
                 if (n >= 2) {

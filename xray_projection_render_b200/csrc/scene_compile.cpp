@@ -928,7 +928,7 @@ static void emit_prim_params(Builder& B, const Node& n) {
                 const double as = std::fabs(scale);
                 const double M2 = B.so_ok ? 1.01 * (2.0 * (B.so_jac2 / as) * (B.so_jac2 / as) + 3.0 * B.so_curv / as) : 0.0;
                 // g1eps: absolute slack added to |grad g . J d| (fp32 evaluation of gradient and Jacobian)
-                B.f4(std::isfinite(M2) ? up32(M2) : 0.0, up32(1e-3 * B.so_jac2), up32(std::fmax(1.0, B.warp_lip)), 0);
+                B.f4(M2 > 0.0 && std::isfinite(M2) ? up32(M2) : 0.0, up32(1e-3 * B.so_jac2), up32(std::fmax(1.0, B.warp_lip)), 0);  // exactly 0 = rule off
             }
             B.d64(p, 6, kF64Gyroid);
             break;
