@@ -34,6 +34,30 @@ def test_full_size_lattice_random_pixels(X, O, scenes):
         assert ref.min() < 0.9  # the sample really crosses the lattice
 
 
+def test_full_size_gyroid_sigmoid_random_pixels(X, O, scenes):
+    """BASELINE config 3 as specified (gyroid + sigmoid warp, 1024x1024 detector, ds = 4e-4: 8700 coarse steps per ray):
+    4 of the 720 views, 4000 random pixels each -- 1.4e8 density() calls through the oracle, every one of which the
+    lane-asynchronous kernel has to classify like the reference (second-order skips, guard band at 1.1x its bound)."""
+    obj, d = str(scenes / "gyroid_example.json"), str(scenes / "deformation_sigmoid.json")
+    sc, osc = X.Scene(obj, d), O.OracleScene(obj, d)
+    ds = sc.auto_ds()
+    res = 1024
+    angles = X.generate_camera_angles(720)
+    picks = [angles[k] for k in (3, 250, 433, 611)]
+    cams = X.cameras_from_angles(picks, R, FOV)
+    img = X.render_scene(sc, cams, res, ds=ds)
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for v, a in enumerate(picks):
+        ij = rng.integers(200, 824, size=(4000, 2))
+        eye, cm = O.camera_from_angles(a["azimuthal"], a["polar"], R)
+        ref, _ = osc.render_pixels(eye, cm, res, FOV, R, ds, ij)
+        got = img[v][ij[:, 0], ij[:, 1]].astype(np.float64)
+        worst = max(worst, float(np.abs(got - ref).max()))
+        assert ref.min() < 0.9
+    assert worst <= TOL_FP32, worst
+
+
 def test_full_size_pillar_random_pixels(X, O, scenes):
     """BASELINE config 5 geometry at its full 4096x4096 detector: one view, random pixels."""
     obj = str(scenes / "pillar_array.json")

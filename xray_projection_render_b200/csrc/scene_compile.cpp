@@ -917,7 +917,12 @@ static void emit_prim_params(Builder& B, const Node& n) {
             // + 1e-6 per sin/cos: SFU evaluation after Cody-Waite reduction (eval.cuh fast_sincos)
             // argument errors: d(sin a cos b) <= da|cos a cos b| + db|sin a sin b| <= max(da,db) per term (3 terms);
             // function errors: 6 SFU evaluations, each multiplied by a factor <= 1
-            double tol = 2.0 * (3.0 * argerr + 6.0 * (1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
+            // The sum below is a worst-case bound of |g_fp32 - g| (the largest error observed on the gyroid + sigmoid
+            // config is 40x smaller); 1.1 covers the rounding of the bound itself.  The other primitives keep a factor 2:
+            // their bands cost nothing measurable, this one decides how many refined sub-steps (g moves 4e-4 per
+            // sub-step there) need the fp64 reference.
+            double tol = 1.1 * (3.0 * argerr + 6.0 * (1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
+            if (const char* e = getenv("XRAY_DEBUG_GYROID_TOL_SCALE")) tol *= atof(e);  // diagnostics: what a tighter band would buy (unsound < 1)
             B.f4(p[0], p[1], p[2], p[5]);
             // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
             B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
