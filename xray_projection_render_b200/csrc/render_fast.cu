@@ -746,6 +746,8 @@ __device__ __forceinline__ void prim_gyroid_so(const float4* __restrict__ q, flo
     }
 }
 
+constexpr int kPendCap = 8;  // deferred guard-band sub-steps per lane; a ninth is settled at once
+
 template <int SHAPE, int INTEG, bool COUNT, int PRIM>
 #ifndef XR_ASYNC_MINBLOCKS
 #define XR_ASYNC_MINBLOCKS 7
@@ -753,11 +755,12 @@ template <int SHAPE, int INTEG, bool COUNT, int PRIM>
 __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_async_kernel(const RenderParams P, const unsigned char* __restrict__ nfine_tab,
                                                                          int i_coll, int i_tess) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles]
+    // layout: [instr | f32 pool] [FastArgs] [ray64 6 x nt doubles] [deferred guard-band sub-steps kPendCap x nt ints]
     const Instr* sI = reinterpret_cast<const Instr*>(smem);
     const float4* sF = reinterpret_cast<const float4*>(smem + (size_t)P.scene.n_instr * sizeof(Instr));
     FastArgs* sA = reinterpret_cast<FastArgs*>(smem + P.smem_prog_bytes);
     double* sRay = reinterpret_cast<double*>(sA + 1);
+    int* pend = reinterpret_cast<int*>(sRay + 6 * kBlockThreads);
     const int tid = threadIdx.x;
     {
         uint4* dst = reinterpret_cast<uint4*>(smem);
@@ -829,6 +832,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
     float accT = 0.0f, cmpT = 0.0f;
     float prev = 0.0f;
     int jf = 0, nf = 0, kf = 0;  // fine replay of interval kf: sub-step jf of nf
+    int np = 0;                  // guard-band fine sub-steps whose fp64 re-evaluation is deferred to the end
     unsigned int n_eval = 0, n_fine = 0, n_fallback = 0, prim_tests = 0;
 
     while (__any_sync(FULL_MASK, jf < nf || k < k1)) {
@@ -933,7 +937,17 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
             if (!has_grid && test) clear = fmaxf(fminf(clr, tess_limit) - 1.0e-5f, 0.0f) * P.skip_m2s;
         }
         rho *= dmf;
-        // Guard-band samples: the fp64 reference decides, at once.  (Parking such lanes until several of a warp wait and
+        // A guard-band sample of a REFINED sub-step feeds nothing but the sum (main.go:186: T += rho*ds), so its fp64
+        // re-evaluation can wait: note (interval, sub-step), add nothing now, and settle all of them after the march,
+        // where one call of the cold function serves every lane of the warp that has one left (max over lanes ~5 calls
+        // instead of one call per band sample of any lane: 22 per warp on the gyroid + sigmoid config, each for 2.7 lanes).
+        if (INTEG == 1 && unc && fine && np < kPendCap) {
+            pend[np * kBlockThreads + tid] = (kf << 4) | nsub;
+            ++np;
+            rho = 0.0f;
+            unc = false;
+        }
+        // Guard-band samples of the coarse lattice decide refinements: the fp64 reference answers at once.  (Parking such lanes until several of a warp wait and
         // serving them with one call was measured: 4x fewer calls, but the parked lanes stretch the warp's critical path --
         // gyroid +1 %, pillar array -24 % at a threshold of 4 lanes.)
         if (__any_sync(FULL_MASK, unc)) {
@@ -980,12 +994,27 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
             k += adv;
         }
     }
+    if (INTEG == 1) {
+        while (__any_sync(FULL_MASK, np > 0)) {  // settle the deferred sub-steps, newest first
+            const bool has = np > 0;
+            const int ent = has ? pend[(np - 1) * kBlockThreads + tid] : 0;
+            const float r = exact_single_cold<PRIM>(P.scene.f64, P.scene.deform, n_deform, sRay, P.s_tab, ent >> 4, ent & 15, P.ds_fine, P.dm,
+                                                    SHAPE == SHAPE_TESS ? tess_f64_idx : -1, prim_f64_idx, cflags);
+            if (has) {
+                --np;
+                XR_KADD(r * wF);
+                if (COUNT && (P.dbg_cause == 0 || (P.dbg_cause & 4))) ++n_fallback;
+            }
+        }
+    }
     const double T = P.flat_field + ((double)accT - (double)cmpT);
     store_pixel(P, view, i, j, valid, exp(-T));
     if (COUNT) add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
 }
 
-size_t async_kernel_smem_bytes(const RenderParams& P) { return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double); }
+size_t async_kernel_smem_bytes(const RenderParams& P) {
+    return (size_t)P.smem_prog_bytes + sizeof(FastArgs) + 6 * kBlockThreads * sizeof(double) + (size_t)kPendCap * kBlockThreads * sizeof(int);
+}
 
 template <int SHAPE, int INTEG, bool COUNT, int PRIM>
 static cudaError_t launch_async_one(const RenderParams& P, const unsigned char* nfine, int i_coll, int i_tess, unsigned int grid,
