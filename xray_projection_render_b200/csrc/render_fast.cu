@@ -832,7 +832,11 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
     float accT = 0.0f, cmpT = 0.0f;
     float prev = 0.0f;
     int jf = 0, nf = 0, kf = 0;  // fine replay of interval kf: sub-step jf of nf
+    // Gyroids only (compile time): their band decides 1.4 samples per ray and their clearance is known everywhere; the
+    // other primitives hardly ever meet a guard band, and the bookkeeping costs the pillar array 5 %.
+    constexpr bool kDefer = INTEG == 1 && PRIM == (int)OP_GYROID;
     int np = 0;                  // guard-band fine sub-steps whose fp64 re-evaluation is deferred to the end
+    const float fine_per_coarse = (float)(P.ds / P.ds_fine);  // 10 (main.go:178), a hair less if the division rounds down
     unsigned int n_eval = 0, n_fine = 0, n_fallback = 0, prim_tests = 0;
 
     while (__any_sync(FULL_MASK, jf < nf || k < k1)) {
@@ -941,7 +945,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
         // re-evaluation can wait: note (interval, sub-step), add nothing now, and settle all of them after the march,
         // where one call of the cold function serves every lane of the warp that has one left (max over lanes ~5 calls
         // instead of one call per band sample of any lane: 22 per warp on the gyroid + sigmoid config, each for 2.7 lanes).
-        if (INTEG == 1 && unc && fine && np < kPendCap) {
+        if (kDefer && unc && fine && np < kPendCap) {
             pend[np * kBlockThreads + tid] = (kf << 4) | nsub;
             ++np;
             rho = 0.0f;
@@ -961,11 +965,22 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
 
         // ---- per-lane bookkeeping ----
         if (fine) {
+            // the clearance holds for refined sub-steps as well: `clear` coarse steps are clear * (DS / ds) sub-steps, and
+            // the skipped ones return this sub-step's rho (a gyroid wall is crossed in 3-4 evaluations instead of 9-10)
+            int adv = 1;
+            if (kDefer && !has_grid) {  // (grid scenes have no clearance next to a surface)
+                const float a = fminf(unc ? 0.0f : clear * fine_per_coarse, (float)(nf - jf));
+                const int n = (int)a;
+                if (n >= 2) {
+                    adv = n;
+                    if (rho != 0.0f) XR_KADD(rho * wF * (float)(n - 1));
+                }
+            }
             XR_KADD(rho * wF);
-            ++jf;
+            jf += adv;
             if (COUNT) {
                 ++n_eval;
-                ++n_fine;
+                n_fine += (unsigned int)adv;
             }
         } else if (act) {
             if (COUNT) ++n_eval;
@@ -994,7 +1009,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
             k += adv;
         }
     }
-    if (INTEG == 1) {
+    if (kDefer) {
         while (__any_sync(FULL_MASK, np > 0)) {  // settle the deferred sub-steps, newest first
             const bool has = np > 0;
             const int ent = has ? pend[(np - 1) * kBlockThreads + tid] : 0;
