@@ -1,11 +1,11 @@
 """CPU model of the lane-asynchronous march for a tessellated gyroid (render_fast.cu render_async_kernel).
 
-Two uses (development aid; needs only numpy and the oracle):
-  * `python tools/async_march_model.py check`  -- runs the kernel's per-lane state machine (fp32 evaluation, guard band,
+Two uses (test infrastructure, like the oracle it checks against; needs only numpy):
+  * `python tests/dev/async_march_model.py check`  -- runs the kernel's per-lane state machine (fp32 evaluation, guard band,
     second-order skip bound, immediate fine replay, fp64 oracle for guard-band samples) on a small image and compares
     transmissions and reference-equivalent sample counts with the oracle.  This is how the skip bound and the state
     machine were validated before any GPU time was spent.
-  * `python tools/async_march_model.py iters`  -- warp iteration counts of the lockstep march (every lane at the same
+  * `python tests/dev/async_march_model.py iters`  -- warp iteration counts of the lockstep march (every lane at the same
     lattice index, skip = warp minimum) against the asynchronous one (max over lanes), with the first-order Lipschitz
     rule and with the second-order rule.  BASELINE config 3 (gyroid + sigmoid, ds = 4e-4): 340 -> 69.
 """
@@ -15,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 from oracle import oracle as O  # noqa: E402
 
@@ -163,10 +163,12 @@ def march(sc: Scene, az, pol, res, ds, rule="second", lockstep_warps=None):
             p = eye + d64[idx] * s
             rho[idx] = sc.osc.density(*p)
             fallbacks += 1
-        # bookkeeping
-        T += np.where(fine, rho.astype(np.float64) * wF, 0)
-        n_fine += fine
-        jf = jf + fine
+        # bookkeeping: refined sub-steps skip with the same clearance (clear coarse steps = 10 * clear sub-steps)
+        af = np.minimum(np.where(unc, 0, clear * f32(10.0)), (nf - jf).astype(f32)).astype(np.int64)
+        advf = np.where(fine & (af >= 2), af, 1)
+        T += np.where(fine, rho.astype(np.float64) * wF * advf, 0)
+        n_fine += np.where(fine, advf, 0)
+        jf = jf + np.where(fine, advf, 0)
         coarse = act & ~fine
         trans = coarse & ((rho == 0) != (prev == 0))
         kf = np.where(trans, k, kf)

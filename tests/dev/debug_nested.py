@@ -1,7 +1,7 @@
 import json, sys
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parents[1]; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT/"tests"))
+ROOT = Path(__file__).resolve().parents[2]; sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT/"tests"))
 import xray_projection_render_b200 as X
 from oracle import oracle as O
 from helpers import gpu_vs_oracle
