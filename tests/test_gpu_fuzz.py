@@ -100,3 +100,48 @@ def test_random_scene(X, O, seed):
     out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=views, res=res, integ=integ, ds=ds, ff=float(rng.choice([0.0, 0.2])),
                                  dm=float(rng.choice([1.0, 0.5, 2.0])))
     assert_parity(out, nref)
+
+
+def rnd_one_primitive_scene(rng):
+    """Scenes the lane-asynchronous kernel takes: exactly one sphere / box / cylinder / gyroid, bare, as the only child of a
+    collection, or as the only child of a tessellated unit cell."""
+    t = rng.choice(["gyroid", "gyroid", "sphere", "box", "cylinder"])
+    wrap = rng.choice(["bare", "coll", "tess", "tess"])
+    cell = rng.uniform(0.35, 0.9, 3) if wrap == "tess" else np.ones(3)
+    lo = rng.uniform(-0.3, 0.0, 3) if wrap == "tess" else -0.5 * np.ones(3)
+    c = list(lo + 0.5 * cell + rng.uniform(-0.1, 0.1, 3) * cell)
+    rho = float(rng.choice([1.0, 0.6, 1.7, -0.4]))
+    s = float(cell.min())
+    if t == "gyroid":
+        p = {"type": t, "center": c, "scale": float(rng.uniform(0.06, 0.2)), "thickness": float(rng.uniform(0.1, 0.7)), "rho": abs(rho)}
+    elif t == "sphere":
+        p = {"type": t, "center": c, "radius": float(rng.uniform(0.1, 0.45) * s), "rho": rho}
+    elif t == "box":
+        p = {"type": t, "center": c, "sides": list(rng.uniform(0.2, 0.8, 3) * cell), "rho": rho}
+    else:
+        p = {"type": t, "p0": list(np.array(c) - rng.uniform(-0.4, 0.4, 3) * cell), "p1": list(np.array(c) + rng.uniform(-0.4, 0.4, 3) * cell),
+             "radius": float(rng.uniform(0.05, 0.25) * s), "rho": rho}
+    if wrap == "bare":
+        return p
+    if wrap == "coll":
+        return {"type": "object_collection", "greedy_dens_eval": bool(rng.random() < 0.5), "objects": [p]}
+    b = rng.uniform(0.5, 0.95, 3)
+    uc = {"objects": {"objects": [p]}, "xmin": lo[0], "xmax": lo[0] + cell[0], "ymin": lo[1], "ymax": lo[1] + cell[1],
+          "zmin": lo[2], "zmax": lo[2] + cell[2]}
+    return {"type": "tessellated_obj_coll", "uc": uc, "xmin": -b[0], "xmax": b[0], "ymin": -b[1], "ymax": b[1], "zmin": -b[2], "zmax": b[2]}
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_one_primitive_scene(X, O, seed):
+    """The per-lane march, the second-order gyroid skip bound under every warp type, refined-interval skipping and the
+    deferred guard-band settling, at steps down to 1e-3 (3480 coarse samples per ray)."""
+    rng = np.random.default_rng(5000 + seed)
+    obj = rnd_one_primitive_scene(rng)
+    deform = rnd_deform(rng)
+    integ = "hierarchical" if rng.random() < 0.75 else "simple"
+    res = int(rng.choice([17, 24, 32]))
+    ds = float(rng.choice([0.02, 0.007, 0.003, 0.001]))
+    views = ((float(rng.uniform(0, 360)), float(rng.uniform(35, 145))),)
+    out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=views, res=res, integ=integ, ds=ds, ff=float(rng.choice([0.0, 0.2])),
+                                 dm=float(rng.choice([1.0, 0.5, 2.0])))
+    assert_parity(out, nref)
