@@ -16,10 +16,11 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e, open(sys.argv[1]).read()[-400:])
 PY
 }
+# optional extra builds to compare: put them under xray_projection_render_b200/lib/variants/*.so (make EXTRA=-D..., then copy the .so)
 V=xray_projection_render_b200/lib/variants
 BARGS="--workload gyroid_sigmoid --views 8"; one gy_async A=1; one gy_lock XRAY_NO_ASYNC=1
-for v in $V/*.so; do one gy_$(basename $v .so) XRAY_CUDA_LIB=$PWD/$v; done
+for v in $V/*.so; do [ -e "$v" ] && one gy_$(basename $v .so) XRAY_CUDA_LIB=$PWD/$v; done
 BARGS="--workload pillar_array --views 8"; one pil_async A=1; one pil_lock XRAY_NO_ASYNC=1
-for v in $V/*.so; do one pil_$(basename $v .so) XRAY_CUDA_LIB=$PWD/$v; done
+for v in $V/*.so; do [ -e "$v" ] && one pil_$(basename $v .so) XRAY_CUDA_LIB=$PWD/$v; done
 BARGS="--workload lattice --views 60"; one lat A=1
 for w in balls box_w_pped lattice_linear lattice_sigmoid cube_w_hole; do BARGS="--workload $w --views 8"; one $w A=1; done
