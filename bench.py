@@ -314,6 +314,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         views = args.views
     if args.res:
         res = args.res
+    if args.integ:
+        integ = args.integ
     angles = rank_views(views * world, rank, world)
     cams = X.cameras_from_angles(angles, R_CAM, FOV)
     n = len(cams)
@@ -497,6 +499,7 @@ def main():
     ap.add_argument("--workload", default="lattice", choices=sorted(WORKLOADS))
     ap.add_argument("--views", type=int, default=0, help="override views per GPU (diagnostics only)")
     ap.add_argument("--res", type=int, default=0, help="override detector size (diagnostics only)")
+    ap.add_argument("--integ", default="", choices=["", "simple", "hierarchical"], help="override the integrator (diagnostics only)")
     ap.add_argument("--volume-n", type=int, default=1024)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
