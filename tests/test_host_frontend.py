@@ -269,3 +269,36 @@ def test_renderer_parameter_validation(X):
     assert out["success"] is False and "ds is 0" in out["error"]  # api.go:96-98
     out = r.render({"input": "x.json", "density_multiplier": 0})
     assert out["success"] is False and "density_multiplier is 0" in out["error"]  # api.go:99-101
+
+
+def _gyroid_records(X, obj, deform):
+    """(second float4, third float4) of the first gyroid's fp32 record in the compiled program (program.h layout)."""
+    blob = X.Scene(obj, deform).program_bytes()
+    hdr = struct.unpack_from("<16I", blob, 0)
+    n_instr, instr_off, f32_off, f32_count = hdr[3], hdr[4], hdr[5], hdr[6]
+    instr = np.frombuffer(blob, dtype=np.uint32, count=n_instr * 8, offset=instr_off).reshape(-1, 8)
+    f32 = np.frombuffer(blob, dtype=np.float32, count=f32_count * 4, offset=f32_off).reshape(-1, 4)
+    run = next(r for r in instr if r[0] == 5)  # OP_GYROID
+    return f32[run[4] + 1], f32[run[4] + 2]
+
+
+def test_gyroid_second_order_bound_in_the_program(X):
+    """The third float4 of a gyroid record carries the second-order skip bound M2 = 1.01 (2 (|J|/scale)^2 + 3 curv/scale)
+    of render_fast.cu prim_gyroid_so.  It must be EXACTLY zero (rule off, first-order Lipschitz bound used) for warp
+    chains without a curvature bound -- a denormal there once switched the rule on with the un-warped ray direction."""
+    cell = {"type": "tessellated_obj_coll", "xmin": -0.7, "xmax": 0.7, "ymin": -0.6, "ymax": 0.6, "zmin": -0.65, "zmax": 0.65,
+            "uc": {"xmin": -1.0, "xmax": 1.0, "ymin": -1.0, "ymax": 1.0, "zmin": -1.0, "zmax": 1.0,
+                   "objects": {"objects": [{"type": "gyroid", "center": [0.0, 0.0, 0.0], "scale": 0.125, "thickness": 0.25, "rho": 0.8}]}}}
+    b, c = _gyroid_records(X, cell, None)
+    assert b[0] == np.float32(8.0) and c[0] == pytest.approx(1.01 * 2 * 64.0, rel=1e-6) and c[2] == pytest.approx(1.0, rel=1e-6)
+    A, L = 0.2, 0.1
+    b, c = _gyroid_records(X, cell, {"type": "sigmoid", "amplitude": A, "center": 0.0, "lengthscale": L, "direction": "z"})
+    jac, curv = 1 + A / (4 * L), A * 0.0962251 / L**2
+    assert c[0] == pytest.approx(1.01 * (2 * (jac / 0.125) ** 2 + 3 * curv / 0.125), rel=1e-6) and c[2] == pytest.approx(jac, rel=1e-6)
+    for d in ({"type": "rigid", "displacements": [0.1, 0.0, 0.0]}, {"type": "linear", "strains": [0.01, 0.0, 0.0, 0.02, 0.0, 0.0]},
+              {"type": "affine", "matrix": [[1.1, 0.0, 0.0], [0.0, 0.9, 0.1], [0.0, 0.0, 1.0]]}):
+        assert _gyroid_records(X, cell, d)[1][0] > 0.0
+    for d in ({"type": "gaussian", "amplitudes": [0.1, 0.0, -0.1], "sigmas": [0.3, 0.4, 0.5], "centers": [0.1, 0.0, -0.2]},
+              {"type": "composed", "deformations": [{"type": "rigid", "displacements": [0.1, 0.0, 0.0]},
+                                                    {"type": "linear", "strains": [0.01, 0.02, 0.03, 0.0, 0.0, 0.05]}]}):
+        assert _gyroid_records(X, cell, d)[1][0] == 0.0  # exactly: the kernel tests `> 0`
