@@ -127,6 +127,12 @@ def _obj_tokens(d: dict, ctx: _Ctx, base_dir: str) -> str:
         # uc.objects is parsed as an ObjectCollection whatever its "type" says (objects.go:481-487)
         return f"tess {b} {ub} {_coll_tokens(uc['objects'], ctx, base_dir, force_greedy=True)}"
     if t == "voxel_grid":
+        if "_array_f32" in d:  # test hook for full-size volumes: fp32 array borrowed without the 2x fp64 copy
+            arr = d["_array_f32"]
+            assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
+            nz, nx, ny = arr.shape
+            ctx.vox.append(arr)
+            return f"voxelf {nx} {ny} {nz} {len(ctx.vox) - 1}"
         if "_array" in d:  # test hook: in-memory volume, layout [z][x][y]
             arr = np.ascontiguousarray(d["_array"], dtype=np.float64)
             nz, nx, ny = arr.shape

@@ -312,7 +312,12 @@ struct TessellatedObjColl : Object {
 // objects.go:789-860
 struct VoxelGrid : Object {
     std::vector<double> Rho;
+    // Test hook for full-size volumes (1024^3): borrow the caller's fp32 array instead of copying it into 8 GiB of
+    // doubles.  Widening fp32 -> fp64 is exact, so Density() returns what it would for the same values held as float64
+    // (which is what the Go host has after loading a float32 .raw, objects.go:935-941).
+    const float* RhoF = nullptr;
     long NX, NY, NZ;
+    inline double at(long idx) const { return RhoF ? (double)RhoF[idx] : Rho[idx]; }
     double Density(double x, double y, double z) const override {
         if (x < -1 || x > 1 || y < -1 || y > 1 || z < -1 || z > 1) return 0.0;
         x = (x + 1) / 2;
@@ -330,15 +335,14 @@ struct VoxelGrid : Object {
         if (y1 >= NY) y1 = NY - 1;
         if (z1 >= NZ) z1 = NZ - 1;
         double wx = x - double(x0), wy = y - double(y0), wz = z - double(z0);
-        const double* R = Rho.data();
-        double v000 = R[z0 * NX * NY + x0 * NY + y0];
-        double v001 = R[z1 * NX * NY + x0 * NY + y0];
-        double v010 = R[z0 * NX * NY + x0 * NY + y1];
-        double v011 = R[z1 * NX * NY + x0 * NY + y1];
-        double v100 = R[z0 * NX * NY + x1 * NY + y0];
-        double v101 = R[z1 * NX * NY + x1 * NY + y0];
-        double v110 = R[z0 * NX * NY + x1 * NY + y1];
-        double v111 = R[z1 * NX * NY + x1 * NY + y1];
+        double v000 = at(z0 * NX * NY + x0 * NY + y0);
+        double v001 = at(z1 * NX * NY + x0 * NY + y0);
+        double v010 = at(z0 * NX * NY + x0 * NY + y1);
+        double v011 = at(z1 * NX * NY + x0 * NY + y1);
+        double v100 = at(z0 * NX * NY + x1 * NY + y0);
+        double v101 = at(z1 * NX * NY + x1 * NY + y0);
+        double v110 = at(z0 * NX * NY + x1 * NY + y1);
+        double v111 = at(z1 * NX * NY + x1 * NY + y1);
         double v00 = v000 * (1 - wz) + v001 * wz;
         double v01 = v010 * (1 - wz) + v011 * wz;
         double v10 = v100 * (1 - wz) + v101 * wz;
@@ -556,7 +560,7 @@ static std::unique_ptr<Object> parse_object(Tok& t) {
         o->UC.GreedyDensEval = true;  // objects.go:487
         return o;
     }
-    if (k == "voxel") {
+    if (k == "voxel" || k == "voxelf") {
         auto o = std::make_unique<VoxelGrid>();
         o->NX = (long)t.num();
         o->NY = (long)t.num();
@@ -567,7 +571,8 @@ static std::unique_ptr<Object> parse_object(Tok& t) {
             return nullptr;
         }
         size_t n = (size_t)o->NX * o->NY * o->NZ;
-        o->Rho.assign(t.vox_data[idx], t.vox_data[idx] + n);
+        if (k == "voxelf") o->RhoF = reinterpret_cast<const float*>(t.vox_data[idx]);  // borrowed: the caller keeps it alive
+        else o->Rho.assign(t.vox_data[idx], t.vox_data[idx] + n);
         return o;
     }
     t.err = "unknown object '" + k + "'";

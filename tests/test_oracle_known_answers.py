@@ -296,3 +296,14 @@ def test_auto_ds_of_bundled_scenes(O, scenes):
     for name, ds in want.items():
         got = O.OracleScene(str(scenes / f"{name}.json")).auto_ds()
         assert abs(got - ds) <= 1e-7, (name, got)
+
+
+def test_borrowed_fp32_volume_equals_copied_fp64_volume(O):
+    """The `_array_f32` hook (full-size 1024^3 tests) must give bit-identical densities to the fp64 copy path."""
+    rng = np.random.default_rng(3)
+    vol = rng.random((9, 7, 11), dtype=np.float32)
+    a = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)})
+    b = O.OracleScene({"type": "voxel_grid", "_array_f32": vol})
+    for x, y, z in rng.uniform(-1.05, 1.05, size=(400, 3)):
+        assert a.density(x, y, z) == b.density(x, y, z)
+    assert a.min_feature_size() == b.min_feature_size()

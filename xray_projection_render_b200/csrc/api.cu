@@ -566,7 +566,10 @@ static int run_job(Job& J) {
     P.out_f64 = J.opts.out_dtype == XRAY_OUT_F64;
     P.stats = J.opts.stats ? C->d_stats : nullptr;
     P.skip_m2s = getenv("XRAY_NO_SKIP") ? 0.0f : (float)(0.999 / (J.ds * std::fmax(1.0, h->warp_lipschitz)));
-    P.dbg_cause = getenv("XRAY_DEBUG_FB_CAUSE") ? atoi(getenv("XRAY_DEBUG_FB_CAUSE")) : 0;
+    P.dbg_cause = 0;
+#ifdef XRAY_DEV_KNOBS
+    if (const char* e = getenv("XRAY_DEBUG_FB_CAUSE")) P.dbg_cause = atoi(e);  // which fallbacks stats[2] counts (development builds)
+#endif
     {
         size_t prog = ((size_t)h->n_instr * 2 + h->f32_count) * 16;
         size_t stack = (size_t)h->save_depth * kBlockThreads * (5 * sizeof(double) + 5 * sizeof(float) + 8 * sizeof(unsigned int));

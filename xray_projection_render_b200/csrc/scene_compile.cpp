@@ -922,7 +922,9 @@ static void emit_prim_params(Builder& B, const Node& n) {
             // their bands cost nothing measurable, this one decides how many refined sub-steps (g moves 4e-4 per
             // sub-step there) need the fp64 reference.
             double tol = 1.1 * (3.0 * argerr + 6.0 * (1.0e-6 + 4.0 * u * (1.0 + 1e-2 * amax)) + 12.0 * u);
-            if (const char* e = getenv("XRAY_DEBUG_GYROID_TOL_SCALE")) tol *= atof(e);  // diagnostics: what a tighter band would buy (unsound < 1)
+#ifdef XRAY_DEV_KNOBS  // development builds only (make EXTRA=-DXRAY_DEV_KNOBS): unsound below 1, never in the release library
+            if (const char* e = getenv("XRAY_DEBUG_GYROID_TOL_SCALE")) tol *= atof(e);
+#endif
             B.f4(p[0], p[1], p[2], p[5]);
             // .w: object-space (max-norm) distance per unit of |g| margin: sum_i |dg/dq_i| <= 3 (max at q = 0)
             B.f4(1.0 / scale, p[4], up32(tol), std::fabs(scale) / 3.03);
@@ -1405,9 +1407,11 @@ static std::atomic<uint64_t> g_scene_counter{1};
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static bool build_blob(XRayScene& sc, std::string& err) {
+#ifdef XRAY_DEV_KNOBS  // grid tuning knobs of development builds; the release library has fixed, tested values
     if (const char* e = getenv("XRAY_GRID_MAX")) g_grid_max = std::max(1, std::min(64, atoi(e)));
     if (const char* e = getenv("XRAY_GRID_MIN_CHILDREN")) g_grid_min_children = std::max(1, atoi(e));
     if (const char* e = getenv("XRAY_GRID_FEAT_SCALE")) g_grid_feat_scale = std::max(0.05, atof(e));
+#endif
     Builder B;
     B.sc = &sc;
     double warp_lip = 1.0;
