@@ -102,7 +102,9 @@ typedef struct {
                                   [0] reference-equivalent samples (density() calls the Go integrator would make)
                                   [1] samples evaluated on the GPU   [2] fp64 re-evaluations in fp32 mode
                                   [3] primitive tests executed       [4] rays
-                                  [5] kernel launches */
+                                  [5] kernel launches
+                                  [6] image tiles the interval renderer handed to the marching kernels
+                                  [7] why (OR of reason bits, render_span.cu) */
     int32_t view_begin;        /* first camera's global view index (for sharding bookkeeping only) */
     int32_t reserved[7];
 } XRayRenderOpts;

@@ -34,6 +34,26 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# The analytic-scene suites run twice: through the interval renderer (render_span.cu, the default for scenes of convex
+# primitives) and with it switched off, so that the marching kernels it falls back on keep their full coverage.
+SPAN_MODULES = {"test_gpu_parity", "test_gpu_fuzz", "test_gpu_properties"}
+
+
+@pytest.fixture(autouse=True)
+def kernel_path(request, monkeypatch):
+    mode = getattr(request, "param", None)
+    if mode == "march":
+        monkeypatch.setenv("XRAY_NO_SPAN", "1")
+    elif mode == "span":
+        monkeypatch.delenv("XRAY_NO_SPAN", raising=False)
+    return mode
+
+
+def pytest_generate_tests(metafunc):
+    if metafunc.module.__name__.split(".")[-1] in SPAN_MODULES and "kernel_path" in metafunc.fixturenames:
+        metafunc.parametrize("kernel_path", ["span", "march"], indirect=True)
+
+
 @pytest.fixture(scope="session")
 def X():
     """The product package; building the in-tree library first if it is missing."""

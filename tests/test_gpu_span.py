@@ -1,0 +1,113 @@
+"""The interval ("span") renderer (csrc/render_span.cu): scenes of convex primitives are rendered by intersecting each ray with
+each candidate child in fp64 and sweeping the interval end points over the reference's sample lattice.  These cases aim at
+what is specific to it: tangent and face-parallel rays, rays inside cell-face planes, more intervals than its per-ray lists
+hold (hand-over to the marching kernels), warps that keep rays straight, and that it really is the path taken."""
+import numpy as np
+import pytest
+
+from helpers import FOV, R, TOL_FP32, TOL_FP64, assert_parity, gpu_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(X, O, obj, deform=None, *, views, res, ds=-1.0, integs=("hierarchical", "simple"), dm=1.0, ff=0.0, max_marched=None):
+    worst = 0.0
+    for integ in integs:
+        out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=views, res=res, integ=integ, ds=ds, dm=dm, ff=ff)
+        assert_parity(out, nref)
+        for prec in ("fp32", "fp64"):
+            st = out[prec][1]
+            assert st["launches"] == 2, "interval renderer + tile-list pass expected"
+            if max_marched is not None:
+                assert st["marched_tiles"] <= max_marched, st
+            worst = max(worst, out[prec][0])
+    return worst
+
+
+def test_span_is_the_default_path_for_convex_scenes(X, O, scenes):
+    for name in ("cube_w_hole", "lattice", "pillar_array", "balls", "box_w_pped"):
+        _check(X, O, str(scenes / f"{name}.json"), views=((77.0, 83.0), (200.0, 101.0)), res=40, max_marched=2)  # (the central ray meets cap planes / sphere centres exactly on a lattice sample)
+    # not eligible: gyroid (not convex), sigmoid warp (bends rays) -> one marching launch
+    sc = X.Scene(str(scenes / "lattice.json"), str(scenes / "deformation_sigmoid.json"))
+    cams = X.cameras_from_angles([(77.0, 83.0)], R, FOV)
+    _, st = X.render_scene(sc, cams, 24, return_stats=True)
+    assert st["launches"] == 1 and st["marched_tiles"] == 0
+
+
+@pytest.mark.parametrize("warp", [
+    {"type": "rigid", "displacements": [0.05, -0.11, 0.07]},
+    {"type": "linear", "strains": [0.08, -0.05, 0.03, 0.02, -0.04, 0.06]},
+    {"type": "affine", "matrix": [[0.9, 0.2, -0.1], [0.05, 1.1, 0.15], [-0.2, 0.1, 0.95]]},
+    {"type": "composed", "deformations": [{"type": "linear", "strains": [0.1, 0.0, -0.05, 0.0, 0.03, 0.0]},
+                                          {"type": "rigid", "displacements": [0.1, 0.0, -0.05]},
+                                          {"type": "affine", "matrix": [[1.0, 0.1, 0.0], [0.0, 1.0, 0.1], [0.1, 0.0, 1.0]]}]},
+])
+def test_affine_warps_keep_rays_straight(X, O, scenes, warp):
+    """deformations.go:87-92, 136-141, 173-175, 269-274: the warp is applied to the ray once instead of to every sample."""
+    for name in ("lattice", "cube_w_hole", "box_w_pped"):
+        _check(X, O, str(scenes / f"{name}.json"), warp, views=((90.0, 90.0), (141.0, 66.0)), res=36, dm=1.4, ff=0.02, max_marched=8)
+
+
+def test_tangent_and_axis_parallel_rays(X, O):
+    """The central ray (az 0, polar 90: the x axis) is tangent to a sphere, runs inside a box face, along a cylinder's axis
+    and through the plane of its cap; the central row and column are parallel to box faces.  Whatever the interval renderer
+    cannot decide it must hand over, and the image must still match."""
+    obj = {"type": "object_collection", "objects": [
+        {"type": "sphere", "center": [0.0, 0.3, 0.0], "radius": 0.3, "rho": 0.5},          # tangent to the x axis
+        {"type": "box", "center": [0.4, -0.2, 0.0], "sides": [0.3, 0.4, 0.5], "rho": 0.4},  # face y = 0 contains it
+        {"type": "cylinder", "p0": [-0.6, 0.0, 0.0], "p1": [-0.2, 0.0, 0.0], "radius": 0.1, "rho": 0.3},  # coaxial
+        {"type": "cylinder", "p0": [0.0, -0.5, 0.0], "p1": [0.0, -0.5, 0.4], "radius": 0.2, "rho": -0.2},  # cap in z = 0
+        {"type": "parallelepiped", "origin": [-0.5, 0.2, -0.3], "v0": [0.3, 0.0, 0.0], "v1": [0.0, 0.3, 0.0], "v2": [0.1, 0.0, 0.3],
+         "rho": 0.6}]}
+    for greedy in (False, True):
+        obj["greedy_dens_eval"] = greedy
+        _check(X, O, obj, views=((0.0, 90.0), (90.0, 90.0), (45.0, 90.0)), res=65, ds=0.013)
+
+
+def test_more_intervals_than_the_lists_hold(X, O):
+    """60 thin plates in a row: rays along the row cross far more intervals than the per-ray lists of the interval renderer
+    hold; those tiles go to the marching kernels (marched_tiles > 0) and the image is still exact."""
+    plates = [{"type": "box", "center": [-0.885 + 0.03 * k, 0.0, 0.0], "sides": [0.012, 0.8, 0.8], "rho": 0.05 + 0.01 * (k % 7)}
+              for k in range(60)]
+    obj = {"type": "object_collection", "objects": plates}
+    out, nref, _ = gpu_vs_oracle(X, O, obj, views=((0.0, 90.0), (60.0, 80.0)), res=48, ds=0.004)
+    assert_parity(out, nref)
+    assert out["fp32"][1]["marched_tiles"] > 0
+
+
+def test_every_period_boundary_direction(X, O):
+    """Tessellation whose cell faces pass through the origin in x, y and z, seen along each axis and along diagonals: rays
+    inside face planes (period decided by 1e-16 quantities), rays through cell edges and corners (several faces crossed
+    at once), negative periods."""
+    uc = {"objects": {"objects": [{"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.12, "rho": 0.9},
+                                  {"type": "cylinder", "p0": [0.0, 0.15, 0.15], "p1": [0.3, 0.15, 0.15], "radius": 0.04, "rho": 0.5},
+                                  {"type": "box", "center": [0.15, 0.0, 0.3], "sides": [0.1, 0.1, 0.1], "rho": 0.7}]},
+          "xmin": 0.0, "xmax": 0.3, "ymin": 0.0, "ymax": 0.3, "zmin": 0.0, "zmax": 0.3}
+    obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.75, "xmax": 0.75, "ymin": -0.6, "ymax": 0.6, "zmin": -0.45, "zmax": 0.9}
+    views = ((0.0, 90.0), (90.0, 90.0), (45.0, 90.0), (180.0, 90.0), (30.0, 60.0), (270.0, 120.0))
+    _check(X, O, obj, views=views, res=33, ds=0.011, max_marched=40)
+
+
+def test_fine_lattice_and_window_edges(X, O):
+    """A very small step (8700 coarse samples, like BASELINE config 3's ds) and objects that stick out of the sample window
+    [R - 1.74, R + 1.74] (clipping at smin / smax, main.go:162-169)."""
+    obj = {"type": "object_collection", "objects": [{"type": "cylinder", "p0": [-2.5, 0.0, 0.1], "p1": [2.5, 0.0, 0.1], "radius": 0.15, "rho": 0.2},
+                                                    {"type": "sphere", "center": [0.0, 1.8, 0.0], "radius": 0.4, "rho": 0.5},
+                                                    {"type": "box", "center": [0.0, 0.0, -0.3], "sides": [4.0, 0.2, 0.1], "rho": -0.1}]}
+    _check(X, O, obj, views=((0.0, 90.0), (90.0, 85.0), (33.0, 90.0)), res=24, ds=0.0004, max_marched=12)
+
+
+def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkeypatch):
+    """Full 1024^2 lattice view and a 1024^2 crop-equivalent of the pillar array: interval renderer versus the marching
+    kernels, which the 1e-4 gate of the rest of the suite already ties to the oracle; same reference-equivalent sample count."""
+    for name, res in (("lattice", 1024), ("pillar_array", 1024)):
+        sc = X.Scene(str(scenes / f"{name}.json"))
+        cams = X.cameras_from_angles([(90.0, 90.0), (123.0, 90.0)], R, FOV)
+        a, sa = X.render_scene(sc, cams, res, return_stats=True)
+        monkeypatch.setenv("XRAY_NO_SPAN", "1")
+        b, sb = X.render_scene(sc, cams, res, return_stats=True)
+        monkeypatch.delenv("XRAY_NO_SPAN")
+        assert np.abs(a.astype(np.float64) - b).max() <= 2e-6
+        assert sa["ref_samples"] == sb["ref_samples"]
+        assert sa["launches"] == 2 and sb["launches"] == 1
+        assert sa["marched_tiles"] <= 0.002 * 2 * (res // 4) * (res // 8), sa  # warp tiles of 4 x 8 pixels

@@ -35,6 +35,9 @@ cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator,
 size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_async(const RenderParams& P, int shape, int integrator, bool count, int prim, const unsigned char* d_nfine,
                                 int i_coll, int i_tess, cudaStream_t stream);
+cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count, const unsigned char* d_nfine, const unsigned char* d_section,
+                               unsigned int section_bytes, unsigned int* d_tile_list, unsigned int* d_tile_count, cudaStream_t stream);
+size_t span_kernel_smem_bytes(unsigned int section_bytes);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
                                      int warp_shape, const unsigned char* occ, cudaStream_t stream);
 size_t volume_brick_count(int nx, int ny, int nz);
@@ -391,6 +394,9 @@ struct DevCtx {
     // empty-space map of the volume (render_volume.cu build_volume_occupancy), two ping-pong buffers
     unsigned char* vol_occ[2] = {nullptr, nullptr};
     size_t vol_occ_cap = 0;
+    // tiles the span renderer hands to the marching kernels: compacted ids (one slot per CTA of a launch) + their count
+    unsigned int* d_tile_list = nullptr;
+    size_t tile_list_cap = 0;
 };
 static std::mutex g_ctx_mu;
 static std::map<int, DevCtx*> g_ctx;
@@ -426,6 +432,9 @@ static void ctx_release(DevCtx* c) {
         c->vol_occ[b] = nullptr;
     }
     c->vol_occ_cap = 0;
+    if (c->d_tile_list) cudaFree(c->d_tile_list);
+    c->d_tile_list = nullptr;
+    c->tile_list_cap = 0;
     for (int b = 0; b < 2; ++b) {
         if (c->d_img[b]) cudaFree(c->d_img[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
@@ -684,16 +693,25 @@ static int run_job(Job& J) {
     const size_t max_batch_bytes = J.out_on_device ? (size_t)1 << 30 : (size_t)64 << 20;
     int max_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)nv, max_batch_bytes / img_bytes));
     unsigned long long n_launches = 0;
-    auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
-        ++n_launches;
-        P.cams = C->d_cams + v0;
-        P.n_views = n;
-        P.out = d_dst;
-        // the grid is one CTA per (view, tile); keep it below 2^31
-        if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
+    // Span renderer (render_span.cu): scenes of convex primitives under no / an affine warp, both precisions.  It flags
+    // the tiles it will not vouch for; the marching kernels below re-render exactly those.
+    bool use_span = h->span_bytes > 0 && !J.fast_volume && !getenv("XRAY_NO_SPAN") && (size_t)P.n_steps * 16 < ((size_t)1 << 26) &&
+                    span_kernel_smem_bytes(h->span_bytes) <= 200 * 1024;
+    if (use_span) {
+        const size_t need = (size_t)max_batch * P.tiles_i * P.tiles_j * 4;  // warp tiles
+        if (need > C->tile_list_cap) {
+            CUJ(7, cudaStreamSynchronize(stream));
+            if (C->d_tile_list) cudaFree(C->d_tile_list);
+            C->d_tile_list = nullptr;
+            C->tile_list_cap = 0;
+            CUJ(3, cudaMalloc(&C->d_tile_list, (need + 1) * sizeof(unsigned int)));  // [0] = count, [1..] = ids
+            C->tile_list_cap = need;
+        }
+    }
+    auto launch_march = [&]() -> cudaError_t {
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
-                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, v0, n), vol_occ, stream);
+                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, (int)(P.cams - C->d_cams), P.n_views), vol_occ, stream);
         if (J.fast_volume)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
@@ -703,6 +721,30 @@ static int run_job(Job& J) {
             return launch_render_fast(P, shape, J.opts.integration, P.stats != nullptr, use_list, single_prim, C->d_nfine, i_coll, i_tess,
                                       stream);
         return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
+    };
+    auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
+        ++n_launches;
+        P.cams = C->d_cams + v0;
+        P.n_views = n;
+        P.out = d_dst;
+        P.tile_list = nullptr;
+        P.tile_count = nullptr;
+        // the grid is one CTA per (view, tile); keep it below 2^31
+        if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
+        if (!use_span) return launch_march();
+        cudaError_t es = launch_render_span(P, J.opts.integration, P.stats != nullptr, C->d_nfine, ds->d_blob + h->span_off, h->span_bytes,
+                                            C->d_tile_list + 1, C->d_tile_list, stream);
+        if (es != cudaSuccess) return es;
+#ifdef XRAY_DEV_KNOBS
+        if (P.dbg_cause == 77) return es;  // leave the interval renderer's hand-over codes in the image
+#endif
+        ++n_launches;
+        P.tile_list = C->d_tile_list + 1;
+        P.tile_count = C->d_tile_list;
+        es = launch_march();
+        P.tile_list = nullptr;
+        P.tile_count = nullptr;
+        return es;
     };
 
     if (J.out_on_device) {

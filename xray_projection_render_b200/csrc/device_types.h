@@ -55,9 +55,14 @@ struct RenderParams {
     float dm_f, ds_f, ds_fine_f;  // fp32 copies for the hot loop (no F2F per iteration)
     float skip_m2s;             // object-space clearance -> number of lattice steps that stay inside it (0 disables skipping)
     int dbg_cause;              // COUNT variants only: count fp64 fallbacks of this cause mask (0 = all)
+    // Second pass after the interval renderer (render_span.cu): when tile_list is set, the grid is small and fixed and the CTAs
+    // loop over the compacted warp-tile entries tile_list[0 .. *tile_count) (entry = (view, tile) id * 4 + warp position).
+    const unsigned int* tile_list;
+    const unsigned int* tile_count;
 };
 
 constexpr int kBlockThreads = 128;
+constexpr unsigned int kTileListGrid = 148 * 8;  // CTAs of a tile-list launch (a few per SM)
 #ifndef XR_WARP_I
 #define XR_WARP_I 4
 #endif

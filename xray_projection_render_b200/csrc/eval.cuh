@@ -718,13 +718,33 @@ __device__ __forceinline__ bool clip_ray(const Ray64& r, const double* lo, const
     return t0 <= t1;
 }
 
-__device__ __forceinline__ void pixel_of_thread(const RenderParams& P, int& view, int& i, int& j) {
+// The kernels render one (view, tile) per CTA, or -- second pass after render_span.cu -- loop over a compacted list of
+// WARP tiles: entry = (view, tile) id * 4 + position of the warp's 32 pixels inside the tile; every warp of a CTA takes
+// its own entry (xr_live_ is false for a warp without one: it walks along with valid == false).
+#define XR_TILE_LOOP_BEGIN(P)                                                                              \
+    const unsigned int xr_n_ = (P).tile_list ? *(P).tile_count : 0u;                                       \
+    const unsigned int xr_end_ = (P).tile_list ? (xr_n_ + 3u) / 4u : blockIdx.x + 1u;                      \
+    const unsigned int xr_stride_ = (P).tile_list ? gridDim.x : 0x40000000u;                               \
+    for (unsigned int xr_vb_ = blockIdx.x; xr_vb_ < xr_end_; xr_vb_ += xr_stride_) {                       \
+        unsigned int xr_block_ = xr_vb_, xr_sub_ = threadIdx.x >> 5;                                       \
+        bool xr_live_ = true;                                                                              \
+        if ((P).tile_list) {                                                                               \
+            const unsigned int q_ = xr_vb_ * 4u + (threadIdx.x >> 5);                                      \
+            xr_live_ = q_ < xr_n_;                                                                         \
+            const unsigned int e_ = xr_live_ ? (P).tile_list[q_] : 0u;                                     \
+            xr_block_ = e_ >> 2;                                                                           \
+            xr_sub_ = e_ & 3u;                                                                             \
+        }
+#define XR_TILE_LOOP_END }
+
+// block: (view, tile) id; sub: which of the tile's 2 x 2 warp positions this warp renders
+__device__ __forceinline__ void pixel_of_thread(const RenderParams& P, unsigned int block, unsigned int sub, int& view, int& i, int& j) {
     const int tiles = P.tiles_i * P.tiles_j;
-    const int b = blockIdx.x;
+    const int b = (int)block;
     view = b / tiles;
     const int t = b - view * tiles;
     const int ti = t / P.tiles_j, tj = t - ti * P.tiles_j;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = (int)sub, lane = threadIdx.x & 31;
     i = ti * kTileI + (w >> 1) * kWarpI + lane / kWarpJ;
     j = tj * kTileJ + (w & 1) * kWarpJ + lane % kWarpJ;
 }

@@ -12,7 +12,7 @@
 namespace xr {
 
 constexpr uint32_t kMagic = 0x58524159u;  // "XRAY"
-constexpr uint32_t kVersion = 6;
+constexpr uint32_t kVersion = 7;
 constexpr int kMaxVoxelSlots = 4;
 constexpr int kMaxSaveDepth = 6;  // nested save frames (collections/tessellations inside collections)
 constexpr int kFrameWords = 8;    // real-typed words per save frame
@@ -98,6 +98,38 @@ struct Header {
     double eps_pos;                 // position error bound assumed by the fp32 tolerances
     double warp_lipschitz;          // object-space displacement per unit world displacement (deformation chain)
     int32_t voxel_dims[kMaxVoxelSlots][4];
+    uint32_t span_off, span_bytes;  // SpanHeader section for the interval ("span") renderer, 0 bytes when the scene has none
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Span section: what render_span.cu needs, in fp64.  Built for scenes that are one collection of CONVEX
+// primitives (sphere, box / cube, parallelepiped, cylinder; <= 64 children), bare or tessellated, under no warp or
+// an affine one (rigid / linear / affine / compositions).  Along a straight ray every such child is ONE interval, so
+// the reference's per-sample loop (main.go:144-199) collapses to a sweep over interval end points.
+// ---------------------------------------------------------------------------------------------------------
+enum SpanFlags : uint32_t { SPAN_GREEDY = 1, SPAN_CLAMPS = 2, SPAN_TESS = 4, SPAN_HAS_WARP = 8 };
+
+struct SpanHeader {
+    uint32_t n_children, flags;
+    uint32_t g[3];                 // candidate grid: cells per period (TESS) / over the region (FLAT)
+    uint32_t n_cells;
+    uint32_t child_off, mask_off;  // byte offsets from the start of the section: SpanChild[n], uint64 mask[n_cells]
+    uint32_t total_bytes, pad;
+    double outer[6];               // lo xyz, hi xyz; inclusive bounds test of objects.go:569 (TESS) / the region (FLAT)
+    double uc_lo[3], uc_d[3];      // unit-cell origin and period (objects.go:570-580); FLAT: region origin and extent
+    double uc_hi[3];               // the unit cell's upper bounds as given (UnitCell.Density's inclusive test, objects.go:459)
+    double warp_m[9], warp_b[3];   // object-space point = warp_m * world + warp_b (row-major), the composed affine warp
+    float f_uc_lo[3], f_inv_cell[3], f_cell[3], f_pad[3];
+};
+
+// 160 bytes per child.  p[]: sphere c(3) r2 | box c(3) h(3) | cylinder p0(3) v(3) 1/(v.v) r2 v.v |
+// parallelepiped o(3) Minv rows (9) rownorm(3).  f[]: fp32 copy for the conservative pre-filter
+// (cylinder p0(3) v(3) 1/(v.v) (r+margin)^2; sphere c(3) (r+margin)^2).
+struct SpanChild {
+    uint32_t type, pad;
+    double rho;
+    double p[15];
+    float f[8];
 };
 
 }  // namespace xr

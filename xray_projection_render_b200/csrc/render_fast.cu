@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         }
     }
 
+    XR_TILE_LOOP_BEGIN(P)
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
-    const bool valid = i < P.res && j < P.res;
+    pixel_of_thread(P, xr_block_, xr_sub_, view, i, j);
+    const bool valid = xr_live_ && i < P.res && j < P.res;
     if (!valid) { i = 0; j = 0; }
     int k0, k1;
     bool hit;
@@ -664,6 +665,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_FAST_MINBLOCKS) render_fast_
         // the count of fine steps is ray independent given the refined intervals; recount exactly
         add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
     }
+    XR_TILE_LOOP_END
 }
 
 
@@ -785,9 +787,10 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
         }
     }
 
+    XR_TILE_LOOP_BEGIN(P)
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
-    const bool valid = i < P.res && j < P.res;
+    pixel_of_thread(P, xr_block_, xr_sub_, view, i, j);
+    const bool valid = xr_live_ && i < P.res && j < P.res;
     if (!valid) { i = 0; j = 0; }
     int k, k1;
     float pcx, pcy, pcz, pdx, pdy, pdz;
@@ -1025,6 +1028,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_ASYNC_MINBLOCKS) render_asyn
     const double T = P.flat_field + ((double)accT - (double)cmpT);
     store_pixel(P, view, i, j, valid, exp(-T));
     if (COUNT) add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, prim_tests, valid ? 1ull : 0ull);
+    XR_TILE_LOOP_END
 }
 
 size_t async_kernel_smem_bytes(const RenderParams& P) {
@@ -1045,8 +1049,9 @@ static cudaError_t launch_async_one(const RenderParams& P, const unsigned char* 
 // One-primitive scenes (prim = OP_CYL / OP_GYROID / OP_SPHERE / OP_BOX, run length 1, no cell-list grid).
 cudaError_t launch_render_async(const RenderParams& P, int shape, int integrator, bool count, int prim, const unsigned char* d_nfine,
                                 int i_coll, int i_tess, cudaStream_t stream) {
-    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
     if (grid == 0) return cudaSuccess;
+    if (P.tile_list) grid = grid < kTileListGrid ? grid : kTileListGrid;
 #define XR_AGO(S, I, C, Q) return launch_async_one<S, I, C, Q>(P, d_nfine, i_coll, i_tess, grid, stream)
 #define XR_APRIM(S, I, C)                                          \
     do {                                                           \
@@ -1093,8 +1098,9 @@ static cudaError_t launch_one(const RenderParams& P, const unsigned char* nfine,
 cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
                                const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream) {
     const size_t smem = fast_kernel_smem_bytes(P);
-    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
     if (grid == 0) return cudaSuccess;
+    if (P.tile_list) grid = grid < kTileListGrid ? grid : kTileListGrid;
 #define XR_GO(S, I, C, L, Q) return launch_one<S, I, C, L, Q>(P, d_nfine, i_coll, i_tess, smem, grid, stream)
 #define XR_PICK2(S, I, C)                                              \
     do {                                                               \

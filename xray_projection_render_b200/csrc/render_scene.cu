@@ -30,9 +30,10 @@ __global__ void __launch_bounds__(kBlockThreads) render_scene_exact_kernel(const
     st.r = reinterpret_cast<double*>(smem + P.smem_prog_bytes);
     st.u = reinterpret_cast<unsigned int*>(st.r + (size_t)P.scene.save_depth * 5 * blockDim.x);
 
+    XR_TILE_LOOP_BEGIN(P)
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
-    const bool valid = i < P.res && j < P.res;
+    pixel_of_thread(P, xr_block_, xr_sub_, view, i, j);
+    const bool valid = xr_live_ && i < P.res && j < P.res;
     const CamDev& cam = P.cams[view];
     const Ray64 ray = make_ray(cam, valid ? i : 0, valid ? j : 0, P.res);
     double s_in, s_out;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_scene_exact_kernel(const
     }
     store_pixel(P, view, i, j, valid, exp(-T));
     add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, 0ull, cnt.prim_tests, valid ? 1ull : 0ull);
+    XR_TILE_LOOP_END
 }
 
 // ---------------------------------------------------------------------------------------
@@ -146,9 +148,10 @@ __global__ void __launch_bounds__(kBlockThreads) render_scene_fast_kernel(const 
     stf.u = reinterpret_cast<unsigned int*>(stf.r + (size_t)P.scene.save_depth * 5 * blockDim.x);
     int* queue = reinterpret_cast<int*>(stf.u + (size_t)P.scene.save_depth * 4 * blockDim.x);
 
+    XR_TILE_LOOP_BEGIN(P)
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
-    const bool valid = i < P.res && j < P.res;
+    pixel_of_thread(P, xr_block_, xr_sub_, view, i, j);
+    const bool valid = xr_live_ && i < P.res && j < P.res;
     if (!valid) { i = 0; j = 0; }
     int k0, k1;
     bool hit;
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_scene_fast_kernel(const 
     store_pixel(P, view, i, j, valid, exp(-T));
     add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, cnt.prim_tests,
               valid ? 1ull : 0ull);
+    XR_TILE_LOOP_END
 }
 
 // ---------------------------------------------------------------------------------------
@@ -276,8 +280,9 @@ size_t scene_kernel_smem_bytes(const RenderParams& P, bool with_queue) {
 
 cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream) {
     const size_t smem = scene_kernel_smem_bytes(P, precision == 0);
-    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
     if (grid == 0) return cudaSuccess;
+    if (P.tile_list) grid = grid < kTileListGrid ? grid : kTileListGrid;
 #define XR_LAUNCH(KERNEL)                                                                             \
     do {                                                                                              \
         cudaError_t e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_fast_kernel(const
                                                                           const float* __restrict__ vol, int nx, int ny,
                                                                           int nz, float tol) {
     int view, i, j;
-    pixel_of_thread(P, view, i, j);
+    pixel_of_thread(P, blockIdx.x, threadIdx.x >> 5, view, i, j);
     const bool valid = i < P.res && j < P.res;
     if (!valid) { i = 0; j = 0; }
     const Ray64 ray = make_ray(P.cams[view], i, j, P.res);

@@ -1402,6 +1402,220 @@ static bool emit_node(Builder& B, const Node& n, bool nosave, uint32_t child_bit
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Span section (program.h SpanHeader): the scene restated for the interval renderer (render_span.cu).
+// Eligible: a bare convex primitive, one collection of <= 64 convex primitives, or a tessellation of such a
+// collection; no warp, or a chain of affine warps (rigid / linear / affine), which keeps rays straight.
+// ---------------------------------------------------------------------------------------------------------
+static double g_span_feat_scale = 2.0;  // candidate-grid cell edge in units of the smallest child feature
+static int g_span_grid_max = 16;
+static double g_span_cells_per_cbrt = 2.5;
+
+static bool span_convex(NodeType t) { return t == N_SPHERE || t == N_BOX || t == N_PPED || t == N_CYL; }
+
+static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
+    out.clear();
+    const Node* coll = nullptr;
+    const Node* tess = nullptr;
+    const Node* bare = nullptr;
+    const Node& root = sc.root;
+    if (span_convex(root.type)) bare = &root;
+    else if (root.type == N_COLL) coll = &root;
+    else if (root.type == N_TESS && root.kids.size() == 1 && root.kids[0].type == N_COLL) {
+        tess = &root;
+        coll = &root.kids[0];
+    } else return false;
+    std::vector<const Node*> kids;
+    if (bare) kids.push_back(bare);
+    else
+        for (const auto& k : coll->kids) {
+            if (!span_convex(k.type)) return false;
+            kids.push_back(&k);
+        }
+    if (kids.empty() || kids.size() > 64) return false;
+
+    SpanHeader H = {};
+    H.n_children = (uint32_t)kids.size();
+    H.flags = (coll && coll->greedy ? SPAN_GREEDY : 0) | (coll ? SPAN_CLAMPS : 0) | (tess ? SPAN_TESS : 0);
+    // the warp chain as one affine map
+    double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, b[3] = {0, 0, 0};
+    for (const auto& d : sc.deforms) {
+        double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+        const double* q = d.d;
+        if (d.type == D_AFFINE) {
+            for (int i = 0; i < 9; ++i) A[i] = q[i];
+        } else if (d.type == D_LINEAR) {  // deformations.go:136-141, strains xx,yy,zz,yz,xz,xy
+            const double E[9] = {q[0], q[5], q[4], q[5], q[1], q[3], q[4], q[3], q[2]};
+            for (int i = 0; i < 9; ++i) A[i] += E[i];
+        } else if (d.type == D_RIGID) {
+            for (int i = 0; i < 3; ++i) t[i] = q[i];
+        } else return false;
+        double M2[9], b2[3];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) M2[r * 3 + c] = A[r * 3 + 0] * M[0 * 3 + c] + A[r * 3 + 1] * M[1 * 3 + c] + A[r * 3 + 2] * M[2 * 3 + c];
+            b2[r] = A[r * 3 + 0] * b[0] + A[r * 3 + 1] * b[1] + A[r * 3 + 2] * b[2] + t[r];
+        }
+        memcpy(M, M2, sizeof(M));
+        memcpy(b, b2, sizeof(b));
+        H.flags |= SPAN_HAS_WARP;
+    }
+    for (int i = 0; i < 9; ++i) {
+        if (!std::isfinite(M[i])) return false;
+        H.warp_m[i] = M[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!std::isfinite(b[i])) return false;
+        H.warp_b[i] = b[i];
+    }
+
+    // region the candidate grid spans
+    double lo[3], hi[3];
+    if (tess) {
+        const double* p = tess->p;
+        const double* uc = p + 6;
+        for (int a = 0; a < 3; ++a) {
+            H.outer[a] = p[2 * a];
+            H.outer[3 + a] = p[2 * a + 1];
+            lo[a] = uc[2 * a];
+            hi[a] = uc[2 * a + 1];
+            if (!(p[2 * a] <= p[2 * a + 1])) return false;
+        }
+    } else {
+        Box3 reg = bare ? node_extent(*bare) : node_nonzero_region(*coll, false);
+        if (reg.empty) return false;
+        for (int a = 0; a < 3; ++a) {
+            // a hair of slack: the region only has to CONTAIN every point of positive density
+            const double m = 1e-9 * (1.0 + std::fmax(std::fabs(reg.lo[a]), std::fabs(reg.hi[a])));
+            lo[a] = reg.lo[a] - m;
+            hi[a] = reg.hi[a] + m;
+            H.outer[a] = lo[a];
+            H.outer[3 + a] = hi[a];
+        }
+    }
+    double ext[3], feat = kInf, cmax = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return false;
+        ext[a] = hi[a] - lo[a];  // objects.go:570: dx := l.UC.Xmax - l.UC.Xmin
+        if (!(ext[a] > 0)) return false;
+        H.uc_lo[a] = lo[a];
+        H.uc_d[a] = ext[a];
+        H.uc_hi[a] = hi[a];
+        cmax = std::fmax(cmax, std::fmax(std::fabs(H.outer[a]), std::fabs(H.outer[3 + a])) + std::fabs(lo[a]) + ext[a]);
+    }
+    if (tess)  // number of periods a ray can cross stays small enough for the 4-bit period codes of the kernel
+        for (int a = 0; a < 3; ++a) {
+            const double n_lo = std::floor((H.outer[a] - lo[a]) / ext[a]), n_hi = std::floor((H.outer[3 + a] - lo[a]) / ext[a]);
+            if (!(n_lo >= -14.0 && n_hi <= 14.0)) return false;  // one period of slack: the walk starts a hair outside the box
+        }
+    for (const Node* k : kids) switch (k->type) {
+            case N_SPHERE: feat = std::fmin(feat, std::fabs(k->p[3])); break;
+            case N_CYL: feat = std::fmin(feat, std::fabs(k->p[6])); break;
+            case N_BOX: feat = std::fmin(feat, 0.5 * std::fmin(std::fabs(k->p[3]), std::fmin(std::fabs(k->p[4]), std::fabs(k->p[5])))); break;
+            default: feat = std::fmin(feat, 0.5 * std::fmin(len3(k->p + 3), std::fmin(len3(k->p + 6), len3(k->p + 9)))); break;
+        }
+    if (!std::isfinite(feat) || !(feat > 0)) feat = std::fmax(ext[0], std::fmax(ext[1], ext[2]));
+    // Cell edge: a walk step costs about two pre-filter tests, so the grid is only as fine as the child count pays for
+    // (one child: a cell per period; the 36 struts of lattice.yaml: 8 cells per axis), and never finer than the features.
+    int g[3];
+    const double emax = std::fmax(ext[0], std::fmax(ext[1], ext[2]));
+    const double cell = std::fmax(g_span_feat_scale * feat, emax / (g_span_cells_per_cbrt * std::cbrt((double)kids.size())));
+    for (int a = 0; a < 3; ++a) g[a] = std::max(1, std::min(g_span_grid_max, (int)std::ceil(ext[a] / cell - 1e-9)));
+    if (kids.size() == 1 && !tess) g[0] = g[1] = g[2] = 1;
+    while ((size_t)g[0] * g[1] * g[2] > 2048) {
+        int a = g[0] >= g[1] && g[0] >= g[2] ? 0 : (g[1] >= g[2] ? 1 : 2);
+        g[a] = (g[a] + 1) / 2;
+    }
+    H.n_cells = (uint32_t)(g[0] * g[1] * g[2]);
+    double cs[3];
+    for (int a = 0; a < 3; ++a) {
+        H.g[a] = (uint32_t)g[a];
+        cs[a] = ext[a] / g[a];
+        H.f_uc_lo[a] = (float)lo[a];
+        H.f_inv_cell[a] = (float)(1.0 / cs[a]);
+        H.f_cell[a] = (float)cs[a];
+    }
+    // A child is listed in every cell within `margin` of it: the kernel walks the grid in fp32 (position error a few
+    // 1e-6 for |x| <= 8) and must never miss a cell the exact ray touches.
+    const double margin = 2e-4 * (1.0 + cmax);
+    std::vector<uint64_t> masks(H.n_cells, 0);
+    for (int iz = 0; iz < g[2]; ++iz)
+        for (int iy = 0; iy < g[1]; ++iy)
+            for (int ix = 0; ix < g[0]; ++ix) {
+                double clo[3] = {lo[0] + ix * cs[0] - margin, lo[1] + iy * cs[1] - margin, lo[2] + iz * cs[2] - margin};
+                double chi[3] = {lo[0] + (ix + 1) * cs[0] + margin, lo[1] + (iy + 1) * cs[1] + margin, lo[2] + (iz + 1) * cs[2] + margin};
+                uint64_t m = 0;
+                for (size_t c = 0; c < kids.size(); ++c)
+                    if (child_touches_cell(*kids[c], clo, chi)) m |= (uint64_t)1 << c;
+                masks[((size_t)iz * g[1] + iy) * g[0] + ix] = m;
+            }
+    std::vector<SpanChild> recs(kids.size());
+    const double fm = margin;  // pre-filter inflation (fp32 evaluation of a quadratic with O(1) coefficients)
+    for (size_t c = 0; c < kids.size(); ++c) {
+        const Node& k = *kids[c];
+        SpanChild& r = recs[c];
+        memset(&r, 0, sizeof(r));
+        const double* p = k.p;
+        switch (k.type) {
+            case N_SPHERE:
+                r.type = OP_SPHERE;
+                r.rho = p[4];
+                for (int i = 0; i < 3; ++i) r.p[i] = p[i], r.f[i] = (float)p[i];
+                r.p[3] = p[3] * p[3];  // objects.go:67: dist2 < Radius*Radius
+                r.f[3] = (float)((std::fabs(p[3]) + fm) * (std::fabs(p[3]) + fm));
+                break;
+            case N_BOX:
+                r.type = OP_BOX;
+                r.rho = p[6];
+                for (int i = 0; i < 3; ++i) r.p[i] = p[i], r.p[3 + i] = 0.5 * p[3 + i];  // objects.go:175: 0.5*Sides[i]
+                break;
+            case N_CYL: {
+                r.type = OP_CYL;
+                r.rho = p[7];
+                double v[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
+                const double vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+                if (!(vv > 0) || !std::isfinite(vv)) return false;  // degenerate cylinder: NaN semantics stay with the point evaluators
+                for (int i = 0; i < 3; ++i) r.p[i] = p[i], r.p[3 + i] = v[i], r.f[i] = (float)p[i], r.f[3 + i] = (float)v[i];
+                r.p[6] = 1.0 / vv;
+                r.p[7] = p[6] * p[6];
+                r.p[8] = vv;
+                r.p[9] = p[6];
+                r.f[6] = (float)(1.0 / vv);
+                r.f[7] = (float)((std::fabs(p[6]) + fm) * (std::fabs(p[6]) + fm));
+                if (p[6] < 0) return false;  // d < r never holds: leave such scenes to the point evaluators
+                break;
+            }
+            default: {
+                r.type = OP_PPED;
+                r.rho = p[12];
+                const double* m = p + 13;  // column-major inverse: row i = (m[i], m[3+i], m[6+i])
+                for (int i = 0; i < 3; ++i) {
+                    r.p[i] = p[i];
+                    r.p[3 + 3 * i + 0] = m[i];
+                    r.p[3 + 3 * i + 1] = m[3 + i];
+                    r.p[3 + 3 * i + 2] = m[6 + i];
+                    r.p[12 + i] = std::fabs(m[i]) + std::fabs(m[3 + i]) + std::fabs(m[6 + i]);
+                    if (!std::isfinite(r.p[12 + i])) return false;
+                }
+                break;
+            }
+        }
+        if (!std::isfinite(r.rho)) return false;
+    }
+    size_t off = (sizeof(SpanHeader) + 15) / 16 * 16;
+    H.child_off = (uint32_t)off;
+    off += recs.size() * sizeof(SpanChild);
+    off = (off + 15) / 16 * 16;
+    H.mask_off = (uint32_t)off;
+    off += masks.size() * sizeof(uint64_t);
+    off = (off + 15) / 16 * 16;
+    H.total_bytes = (uint32_t)off;
+    out.assign(off, 0);
+    memcpy(out.data(), &H, sizeof(H));
+    memcpy(out.data() + H.child_off, recs.data(), recs.size() * sizeof(SpanChild));
+    memcpy(out.data() + H.mask_off, masks.data(), masks.size() * sizeof(uint64_t));
+    return true;
+}
+
 static std::atomic<uint64_t> g_scene_counter{1};
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1458,6 +1672,17 @@ static bool build_blob(XRayScene& sc, std::string& err) {
     h.deform_off = (uint32_t)off;
     h.n_deform = (uint32_t)drecs.size();
     off = align_up(off + drecs.size() * sizeof(DeformRec), 16);
+    std::vector<uint8_t> span;
+#ifdef XRAY_DEV_KNOBS
+    if (const char* e = getenv("XRAY_SPAN_FEAT_SCALE")) g_span_feat_scale = std::max(0.25, atof(e));
+    if (const char* e = getenv("XRAY_SPAN_GRID_MAX")) g_span_grid_max = std::max(1, std::min(32, atoi(e)));
+    if (const char* e = getenv("XRAY_SPAN_CELLS_PER_CBRT")) g_span_cells_per_cbrt = std::max(0.1, atof(e));
+#endif
+    if (build_span(sc, span)) {
+        h.span_off = (uint32_t)off;
+        h.span_bytes = (uint32_t)span.size();
+        off = align_up(off + span.size(), 16);
+    }
     h.total_bytes = (uint32_t)off;
     h.save_depth = (uint32_t)B.save_depth_max;
     h.n_voxel_slots = (uint32_t)sc.n_vox;
@@ -1489,6 +1714,7 @@ static bool build_blob(XRayScene& sc, std::string& err) {
     if (!B.f64.empty()) memcpy(sc.blob.data() + h.f64_off, B.f64.data(), B.f64.size() * sizeof(double));
     if (!B.grids.empty()) memcpy(sc.blob.data() + h.grid_off, B.grids.data(), B.grids.size() * sizeof(uint64_t));
     if (!drecs.empty()) memcpy(sc.blob.data() + h.deform_off, drecs.data(), drecs.size() * sizeof(DeformRec));
+    if (!span.empty()) memcpy(sc.blob.data() + h.span_off, span.data(), span.size());
     return true;
 }
 
