@@ -36,7 +36,8 @@ size_t fast_kernel_smem_bytes(const RenderParams& P);
 cudaError_t launch_render_async(const RenderParams& P, int shape, int integrator, bool count, int prim, const unsigned char* d_nfine,
                                 int i_coll, int i_tess, cudaStream_t stream);
 cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count, const unsigned char* d_nfine, const unsigned char* d_section,
-                               unsigned int section_bytes, unsigned int* d_tile_list, unsigned int* d_tile_count, cudaStream_t stream);
+                               unsigned int section_bytes, unsigned int* d_tile_list, unsigned int* d_tile_count, unsigned int* d_bins,
+                               unsigned int bin_cap, unsigned int n_instances, cudaStream_t stream);
 size_t span_kernel_smem_bytes(unsigned int section_bytes);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
                                      int warp_shape, const unsigned char* occ, cudaStream_t stream);
@@ -397,6 +398,9 @@ struct DevCtx {
     // tiles the span renderer hands to the marching kernels: compacted ids (one slot per CTA of a launch) + their count
     unsigned int* d_tile_list = nullptr;
     size_t tile_list_cap = 0;
+    // screen-space bins of the span renderer: per (view, tile) a count and bin_cap instance codes
+    unsigned int* d_bins = nullptr;
+    size_t bins_cap_words = 0;
 };
 static std::mutex g_ctx_mu;
 static std::map<int, DevCtx*> g_ctx;
@@ -435,6 +439,9 @@ static void ctx_release(DevCtx* c) {
     if (c->d_tile_list) cudaFree(c->d_tile_list);
     c->d_tile_list = nullptr;
     c->tile_list_cap = 0;
+    if (c->d_bins) cudaFree(c->d_bins);
+    c->d_bins = nullptr;
+    c->bins_cap_words = 0;
     for (int b = 0; b < 2; ++b) {
         if (c->d_img[b]) cudaFree(c->d_img[b]);
         if (c->h_pin[b]) cudaFreeHost(c->h_pin[b]);
@@ -704,8 +711,52 @@ static int run_job(Job& J) {
             if (C->d_tile_list) cudaFree(C->d_tile_list);
             C->d_tile_list = nullptr;
             C->tile_list_cap = 0;
-            CUJ(3, cudaMalloc(&C->d_tile_list, (need + 1) * sizeof(unsigned int)));  // [0] = count, [1..] = ids
+            CUJ(3, cudaMalloc(&C->d_tile_list, (need + 2) * sizeof(unsigned int)));  // [0] = count, [1] = work counter, [2..] = ids
             C->tile_list_cap = need;
+        }
+    }
+    // Screen-space bins: un-warped scenes seen by ordinary pinhole cameras (orthonormal axes, the eye in the translation column)
+    // that stand clear of the scene; anything else walks the candidate grid per ray.
+    unsigned int bin_cap = 0, n_instances = 0;
+    if (use_span && !getenv("XRAY_SPAN_NO_BINS")) {
+        const SpanHeader* sh = (const SpanHeader*)(J.scene->blob.data() + h->span_off);
+        bool ok = !(sh->flags & SPAN_HAS_WARP);
+        for (int v = 0; v < nv && ok; ++v) {
+            const XRayCameraParams64& c = J.cams[J.views[v]];
+            const double* m = c.view;
+            for (int a = 0; a < 3 && ok; ++a) {
+                for (int b = a; b < 3 && ok; ++b) {
+                    const double d = m[0 * 4 + a] * m[0 * 4 + b] + m[1 * 4 + a] * m[1 * 4 + b] + m[2 * 4 + a] * m[2 * 4 + b];
+                    ok = std::fabs(d - (a == b ? 1.0 : 0.0)) < 1e-6;
+                }
+                ok = ok && std::fabs(m[a * 4 + 3] - c.eye[a]) < 1e-9 && m[12 + a] == 0.0;
+            }
+            ok = ok && m[15] == 1.0;
+            // depth of the nearest corner of the scene's box along the optical axis (camera looks down -z)
+            double dmin = 1e300;
+            for (int q = 0; q < 8 && ok; ++q) {
+                double d = 0.0;
+                for (int a = 0; a < 3; ++a) d -= m[a * 4 + 2] * (sh->outer[(q >> a & 1) ? 3 + a : a] - m[a * 4 + 3]);
+                dmin = std::fmin(dmin, d);
+            }
+            ok = ok && dmin > 0.25;
+        }
+        if (ok) {
+            n_instances = sh->n_periods * sh->n_children;
+            bin_cap = std::min<unsigned int>(64u, n_instances);
+            const size_t words = (size_t)max_batch * P.tiles_i * P.tiles_j * (1 + (size_t)bin_cap);
+            if (words * sizeof(unsigned int) > ((size_t)1 << 30)) bin_cap = 0;  // never more than 1 GiB of bins
+            else if (words > C->bins_cap_words) {
+                CUJ(7, cudaStreamSynchronize(stream));
+                if (C->d_bins) cudaFree(C->d_bins);
+                C->d_bins = nullptr;
+                C->bins_cap_words = 0;
+                if (cudaMalloc(&C->d_bins, words * sizeof(unsigned int)) == cudaSuccess) C->bins_cap_words = words;
+                else {
+                    cudaGetLastError();
+                    bin_cap = 0;
+                }
+            }
         }
     }
     auto launch_march = [&]() -> cudaError_t {
@@ -733,13 +784,13 @@ static int run_job(Job& J) {
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
         if (!use_span) return launch_march();
         cudaError_t es = launch_render_span(P, J.opts.integration, P.stats != nullptr, C->d_nfine, ds->d_blob + h->span_off, h->span_bytes,
-                                            C->d_tile_list + 1, C->d_tile_list, stream);
+                                            C->d_tile_list + 2, C->d_tile_list, bin_cap ? C->d_bins : nullptr, bin_cap, n_instances, stream);
         if (es != cudaSuccess) return es;
 #ifdef XRAY_DEV_KNOBS
         if (P.dbg_cause == 77) return es;  // leave the interval renderer's hand-over codes in the image
 #endif
         ++n_launches;
-        P.tile_list = C->d_tile_list + 1;
+        P.tile_list = C->d_tile_list + 2;
         P.tile_count = C->d_tile_list;
         es = launch_march();
         P.tile_list = nullptr;

@@ -115,6 +115,8 @@ struct SpanHeader {
     uint32_t n_cells;
     uint32_t child_off, mask_off;  // byte offsets from the start of the section: SpanChild[n], uint64 mask[n_cells]
     uint32_t total_bytes, pad;
+    int32_t n_lo[3], n_hi[3];      // periods that meet the outer box, per axis (FLAT: 0..0)
+    uint32_t n_periods, pad2;      // their number, (n_hi - n_lo + 1) multiplied out
     double outer[6];               // lo xyz, hi xyz; inclusive bounds test of objects.go:569 (TESS) / the region (FLAT)
     double uc_lo[3], uc_d[3];      // unit-cell origin and period (objects.go:570-580); FLAT: region origin and extent
     double uc_hi[3];               // the unit cell's upper bounds as given (UnitCell.Density's inclusive test, objects.go:459)
@@ -122,14 +124,16 @@ struct SpanHeader {
     float f_uc_lo[3], f_inv_cell[3], f_cell[3], f_pad[3];
 };
 
-// 160 bytes per child.  p[]: sphere c(3) r2 | box c(3) h(3) | cylinder p0(3) v(3) 1/(v.v) r2 v.v |
+// 184 bytes per child.  p[]: sphere c(3) r2 | box c(3) h(3) | cylinder p0(3) v(3) 1/(v.v) r2 v.v |
 // parallelepiped o(3) Minv rows (9) rownorm(3).  f[]: fp32 copy for the conservative pre-filter
-// (cylinder p0(3) v(3) 1/(v.v) (r+margin)^2; sphere c(3) (r+margin)^2).
+// (cylinder p0(3) v(3) 1/(v.v) (r+margin)^2; sphere / box / parallelepiped: bounding sphere c(3) (R+margin)^2).
+// bs[]: bounding sphere c(3) R+margin (cylinder: R = r + margin around each end point, i.e. a capsule) for screen-space binning.
 struct SpanChild {
     uint32_t type, pad;
     double rho;
     double p[15];
     float f[8];
+    float bs[4];
 };
 
 }  // namespace xr

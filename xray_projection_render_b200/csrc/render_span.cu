@@ -25,18 +25,33 @@ namespace xr {
 #ifndef XR_SPAN_MINBLOCKS
 #define XR_SPAN_MINBLOCKS 4
 #endif
+#ifndef XR_SPAN_PERSISTENT
+#define XR_SPAN_PERSISTENT 0
+#endif
+#if XR_SPAN_PERSISTENT
+#define XR_SPAN_NEXT continue
+#else
+#define XR_SPAN_NEXT return
+#endif
+#ifndef XR_SPAN_CAPMAX
+#define XR_SPAN_CAPMAX 64
+#endif
 // Per-ray list capacity (candidates that survive the pre-filter = intervals at most): whatever fits the shared memory a CTA may
 // use at XR_SPAN_MINBLOCKS CTAs per SM, at most 64.
-constexpr int kSpanCapMax = 64;
+constexpr int kSpanCapMax = XR_SPAN_CAPMAX;
 constexpr double kZone = 1.0e-11; // half-width (in s) of the doubt zone around every end point
 
 struct SpanArgs {
     const unsigned char* section;  // device copy of the SpanHeader section
     unsigned int section_bytes;
     unsigned int* tile_list;       // out: warp tiles ((view, tile) id * 4 + warp position) with a ray that needs the marching kernels
-    unsigned int* tile_count;      // out: their number (zeroed before the launch)
+    unsigned int* tile_count;      // out: their number (zeroed before the launch); tile_count[1] = the work counter of the launch
     unsigned int total_items;      // warp tiles of the launch = views * tiles * 4
     int cap;                       // per-ray list capacity
+    // screen-space bins (span_bin_kernel): per (view, tile) the (period, child) instances whose projection meets the tile
+    const unsigned int* bin_counts;  // null = no bins: every ray walks the candidate grid
+    const unsigned int* bin_lists;
+    unsigned int bin_cap;
 };
 
 static int span_list_cap(unsigned int section_bytes) {
@@ -251,10 +266,23 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
     const unsigned int flags = H.flags;
     const bool tess = (flags & SPAN_TESS) != 0u;
 
-    // Persistent warps: warp g of the grid renders the warp tiles g, g + G, g + 2G, ... (32 pixels each, the same 4 x 8
-    // footprint the marching kernels use); nothing below synchronises beyond the warp.
-    const unsigned int n_warps = gridDim.x * (kBlockThreads / 32);
-    for (unsigned int item = blockIdx.x * (kBlockThreads / 32) + (tid >> 5); item < SA.total_items; item += n_warps) {
+    // Persistent warps: every warp of the grid draws warp tiles (32 pixels, the same 4 x 8 footprint the marching kernels
+    // use) from a global counter, four at a time (= one CTA tile of the marching kernels), until none are left; rays differ
+    // a lot in cost (most miss the object), so a fixed assignment would leave warps idle.  Nothing below synchronises beyond
+    // the warp.
+#if XR_SPAN_PERSISTENT
+    constexpr unsigned int kChunk = 4;
+    for (;;) {
+    unsigned int base = 0u;
+    if ((tid & 31) == 0) base = atomicAdd(SA.tile_count + 1, kChunk);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (base >= SA.total_items) break;
+    for (unsigned int item = base; item < min(base + kChunk, SA.total_items); ++item) {
+#else
+    {
+    {
+    const unsigned int item = blockIdx.x * (kBlockThreads / 32) + (tid >> 5);
+#endif
     int view, i, j;
     pixel_of_thread(P, item >> 2, item & 3u, view, i, j);
     const bool valid = i < P.res && j < P.res;
@@ -323,12 +351,68 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         }
     }
 
-    // ---- phase 1: fp32 walk through the candidate grid; survivors of the pre-filter go to cand[] ----
+    // ---- phase 1: candidates.  Either the tile's screen-space bin (one list per 8 x 16 pixel tile, built per launch by
+    // span_bin_kernel) or, without one, an fp32 walk of this ray through the candidate grid.  Either way every candidate
+    // goes through a conservative fp32 pre-filter and the survivors land in cand[]. ----
     int ncand = 0;
     bool overflow = false;
     const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
     const float fcx = (float)(cx - H.uc_lo[0]), fcy = (float)(cy - H.uc_lo[1]), fcz = (float)(cz - H.uc_lo[2]);  // relative to the cell origin
-    const int n_pass = hit ? (deg_axis >= 0 ? 2 : 1) : 0;  // a ray inside a face plane walks the cells on either side of it
+    const float fta = (float)ta, ftb = (float)tb;
+    const float fA = fdx * fdx + fdy * fdy + fdz * fdz;
+    // child c of the period coded in pcode; (qx, qy, qz) = the ray centre relative to that period's copy of the cell
+    auto test_and_push = [&](int c, int pcode, float qx, float qy, float qz) {
+        const SpanChild& K = ch[c];
+        bool pass = true;
+        const float wx = qx - K.f[0], wy = qy - K.f[1], wz = qz - K.f[2];
+        float A = fA, B = wx * fdx + wy * fdy + wz * fdz, C = wx * wx + wy * wy + wz * wz;
+        float dv = 0.0f, wv = 0.0f, ivv = 0.0f;
+        if (K.type == OP_CYL) {  // the infinite cylinder, inflated
+            dv = fdx * K.f[3] + fdy * K.f[4] + fdz * K.f[5];
+            wv = wx * K.f[3] + wy * K.f[4] + wz * K.f[5];
+            ivv = K.f[6];
+            A -= dv * dv * ivv;
+            B -= wv * dv * ivv;
+            C -= wv * wv * ivv;
+            C -= K.f[7];
+        } else {  // the sphere itself / the bounding sphere of a box or parallelepiped, inflated
+            C -= K.f[3];
+        }
+        const float disc = B * B - A * C;
+        if (disc < -2.0e-6f * (1.0f + B * B)) pass = false;
+        else {
+            const float iA = 1.0f / fmaxf(A, 1.0e-12f);
+            const float th = sqrtf(fmaxf(disc, 0.0f)) * iA + 1.0e-3f, tm = -B * iA;
+            if (tm + th < fta || tm - th > ftb) pass = false;
+            if (K.type == OP_CYL) {
+                const float cm = (wv + tm * dv) * ivv, hc = th * fabsf(dv) * ivv + 1.0e-3f;
+                if (cm + hc < 0.0f || cm - hc > 1.0f) pass = false;
+            }
+        }
+        if (pass) {
+            if (ncand < cap) cand[ncand * kBlockThreads + tid] = (unsigned int)c | (unsigned int)pcode;
+            else overflow = true;
+            ++ncand;
+        }
+    };
+    bool walk = hit;
+    if (SA.bin_counts) {  // uniform
+        const unsigned int nb = __ldg(SA.bin_counts + (item >> 2));
+        if (nb <= SA.bin_cap) {  // (a bin that overflowed is not used: those tiles walk)
+            walk = false;
+            const unsigned int* __restrict__ bl = SA.bin_lists + (size_t)(item >> 2) * SA.bin_cap;
+            const float ucdx = (float)H.uc_d[0], ucdy = (float)H.uc_d[1], ucdz = (float)H.uc_d[2];
+            const float ulx = H.f_uc_lo[0], uly = H.f_uc_lo[1], ulz = H.f_uc_lo[2];
+            for (unsigned int q = 0; q < nb; ++q) {
+                const unsigned int code = __ldg(bl + q);
+                const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
+                if (hit)
+                    test_and_push((int)(code & 63u), (int)(code & ~63u), fcx - (float)px * ucdx + ulx, fcy - (float)py * ucdy + uly,
+                                  fcz - (float)pz * ucdz + ulz);
+            }
+        }
+    }
+    const int n_pass = walk ? (deg_axis >= 0 ? 2 : 1) : 0;  // a ray inside a face plane walks the cells on either side of it
     const int max_pass = __reduce_max_sync(FULL_MASK, n_pass);
     for (int pass = 0; pass < max_pass; ++pass) {
         if (pass >= n_pass) continue;
@@ -337,7 +421,6 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         const float csx = H.f_cell[0], csy = H.f_cell[1], csz = H.f_cell[2];
         const float ucdx = (float)H.uc_d[0], ucdy = (float)H.uc_d[1], ucdz = (float)H.uc_d[2];
         const float ulx = H.f_uc_lo[0], uly = H.f_uc_lo[1], ulz = H.f_uc_lo[2];
-        const float fta = (float)ta, ftb = (float)tb;
         const float slack = 2.0e-4f * (1.0f + fabsf(fcx) + fabsf(fcy) + fabsf(fcz));
         const float t_begin = fta - slack, t_end = ftb + slack;
         const float ifx = 1.0f / fdx, ify = 1.0f / fdy, ifz = 1.0f / fdz;
@@ -349,7 +432,6 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         if (deg_axis == 2) iz = deg_m * gz - 1 + pass;
         const float tie_d = 0.25f * slack;
         unsigned long long done = 0ull;
-        const float fA = fdx * fdx + fdy * fdy + fdz * fdz;
 
         // visit one grid cell (local index l*, period p*): new children of its mask are pre-filtered and pushed
         // (`done` = the children already seen in the current period; the walk clears it when it enters another period.  The
@@ -369,40 +451,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             while (nw) {
                 const int c = __ffsll((long long)nw) - 1;
                 nw &= nw - 1ull;
-                const SpanChild& K = ch[c];
-                bool pass = true;
-                if (K.type == OP_CYL || K.type == OP_SPHERE) {
-                    const float wx = qx - K.f[0], wy = qy - K.f[1], wz = qz - K.f[2];
-                    float A = fA, B = wx * fdx + wy * fdy + wz * fdz, C = wx * wx + wy * wy + wz * wz;
-                    float dv = 0.0f, wv = 0.0f, ivv = 0.0f;
-                    if (K.type == OP_CYL) {
-                        dv = fdx * K.f[3] + fdy * K.f[4] + fdz * K.f[5];
-                        wv = wx * K.f[3] + wy * K.f[4] + wz * K.f[5];
-                        ivv = K.f[6];
-                        A -= dv * dv * ivv;
-                        B -= wv * dv * ivv;
-                        C -= wv * wv * ivv;
-                        C -= K.f[7];
-                    } else {
-                        C -= K.f[3];
-                    }
-                    const float disc = B * B - A * C;
-                    if (disc < -2.0e-6f * (1.0f + B * B)) pass = false;
-                    else {
-                        const float iA = 1.0f / fmaxf(A, 1.0e-12f);
-                        const float th = sqrtf(fmaxf(disc, 0.0f)) * iA + 1.0e-3f, tm = -B * iA;
-                        if (tm + th < fta || tm - th > ftb) pass = false;
-                        if (K.type == OP_CYL) {
-                            const float cm = (wv + tm * dv) * ivv, hc = th * fabsf(dv) * ivv + 1.0e-3f;
-                            if (cm + hc < 0.0f || cm - hc > 1.0f) pass = false;
-                        }
-                    }
-                }
-                if (pass) {
-                    if (ncand < cap) cand[ncand * kBlockThreads + tid] = (unsigned int)c | (unsigned int)pcode;
-                    else overflow = true;
-                    ++ncand;
-                }
+                test_and_push(c, pcode, qx, qy, qz);
             }
         };
 
@@ -630,17 +679,100 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
 #ifdef XRAY_DEV_KNOBS
     if (P.dbg_cause == 77) {  // development builds: show which rays are handed over, and why
         store_pixel(P, view, i, j, valid, bad ? -(double)doubt : exp(-(P.flat_field + T)));
-        continue;
+        XR_SPAN_NEXT;
     }
 #endif
     store_pixel(P, view, i, j, valid, exp(-(P.flat_field + T)));
     if (COUNT && !tile_bad)
         add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, (unsigned long long)niv, 0ull, prim_tests, valid ? 1ull : 0ull);
-    }  // warp tiles
+    }  // warp tiles of the chunk
+    }  // chunks
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Screen-space binning.  Which children can a ray meet?  All rays of a view leave one point, so the answer is a 2-D
+// question on the detector: project every (period, child) instance of the scene -- its bounding sphere, or for a
+// cylinder the capsule around its axis -- and list it in the 8 x 16 pixel tiles its projection touches.  One warp per
+// instance and view; lanes stride over the tiles of the projection's bounding box.  Conservative by construction (a
+// sphere of radius R at depth D around the image point p projects inside a disc of radius f R / (D - R) * sqrt(1 + |p|^2 / f^2);
+// the bins use the larger (1 + |p|^2 / f^2), 2 % more and two pixel pitches of padding); a bin that overflows its
+// capacity is ignored by the renderer, which then walks the candidate grid for that tile instead.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads) span_bin_kernel(const RenderParams P, const unsigned char* __restrict__ section,
+                                                                 unsigned int* __restrict__ counts, unsigned int* __restrict__ lists,
+                                                                 unsigned int cap) {
+    const SpanHeader& H = *reinterpret_cast<const SpanHeader*>(section);
+    const SpanChild* __restrict__ ch = reinterpret_cast<const SpanChild*>(section + H.child_off);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int inst = blockIdx.x * (kBlockThreads / 32) + (threadIdx.x >> 5);
+    if (inst >= H.n_periods * H.n_children) return;
+    const int c = (int)(inst % H.n_children);
+    const unsigned int pidx = inst / H.n_children;
+    const int nx = H.n_hi[0] - H.n_lo[0] + 1, ny = H.n_hi[1] - H.n_lo[1] + 1;
+    const int px = H.n_lo[0] + (int)(pidx % (unsigned int)nx), py = H.n_lo[1] + (int)((pidx / (unsigned int)nx) % (unsigned int)ny),
+              pz = H.n_lo[2] + (int)(pidx / (unsigned int)(nx * ny));
+    const int view = blockIdx.y;
+    const CamDev& cam = P.cams[view];
+    const SpanChild& K = ch[c];
+    const float sx = (float)px * (float)H.uc_d[0], sy = (float)py * (float)H.uc_d[1], sz = (float)pz * (float)H.uc_d[2];
+    float ax, ay, az, bx, by, bz;
+    if (K.type == OP_CYL) {
+        ax = K.f[0] + sx; ay = K.f[1] + sy; az = K.f[2] + sz;
+        bx = ax + K.f[3]; by = ay + K.f[4]; bz = az + K.f[5];
+    } else {
+        ax = bx = K.bs[0] + sx; ay = by = K.bs[1] + sy; az = bz = K.bs[2] + sz;
+    }
+    const float R = K.bs[3];
+    // camera coordinates: X = V3 * cam + t  =>  cam = V3^T (X - t), V3 orthonormal (checked by the caller)
+    const float tx = (float)cam.view[3], ty = (float)cam.view[7], tz = (float)cam.view[11];
+    float ca[3], cb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v0 = (float)cam.view[0 * 4 + k], v1 = (float)cam.view[1 * 4 + k], v2 = (float)cam.view[2 * 4 + k];
+        ca[k] = v0 * (ax - tx) + v1 * (ay - ty) + v2 * (az - tz);
+        cb[k] = v0 * (bx - tx) + v1 * (by - ty) + v2 * (bz - tz);
+    }
+    const float f = (float)cam.f, h = 0.5f * (float)P.res, pitch = 1.0f / h;
+    const float Da = -ca[2], Db = -cb[2], Dmin = fminf(Da, Db);
+    int ti_lo = 0, ti_hi = P.tiles_i - 1, tj_lo = 0, tj_hi = P.tiles_j - 1;
+    float pax = 0.0f, pay = 0.0f, pbx = 0.0f, pby = 0.0f, Rn = 3.0e38f;
+    if (Dmin - R > 0.05f) {  // otherwise (an instance at or behind the eye) every tile gets it
+        pax = f * ca[0] / Da; pay = f * ca[1] / Da;
+        pbx = f * cb[0] / Db; pby = f * cb[1] / Db;
+        const float pm2 = fmaxf(pax * pax + pay * pay, pbx * pbx + pby * pby);
+        Rn = 1.02f * f * R / (Dmin - R) * (1.0f + pm2 / (f * f)) + 2.0f * pitch;
+        const float xmin = fminf(pax, pbx) - Rn, xmax = fmaxf(pax, pbx) + Rn, ymin = fminf(pay, pby) - Rn, ymax = fmaxf(pay, pby) + Rn;
+        // tile ti holds the pixels i in [ti * kTileI, ti * kTileI + kTileI - 1], pixel i sits at i * pitch - 1 (main.go:463)
+        ti_lo = max(0, (int)ceilf(((xmin + 1.0f) * h - (float)(kTileI - 1)) / (float)kTileI));
+        ti_hi = min(P.tiles_i - 1, (int)floorf((xmax + 1.0f) * h / (float)kTileI));
+        tj_lo = max(0, (int)ceilf(((ymin + 1.0f) * h - (float)(kTileJ - 1)) / (float)kTileJ));
+        tj_hi = min(P.tiles_j - 1, (int)floorf((ymax + 1.0f) * h / (float)kTileJ));
+    }
+    if (ti_hi < ti_lo || tj_hi < tj_lo) return;
+    const int wj = tj_hi - tj_lo + 1, n = (ti_hi - ti_lo + 1) * wj;
+    const unsigned int code = (unsigned int)c | (unsigned int)(((px + 16) << 6) | ((py + 16) << 11) | ((pz + 16) << 16));
+    const float hd = 0.5f * pitch * sqrtf((float)((kTileI - 1) * (kTileI - 1) + (kTileJ - 1) * (kTileJ - 1)));
+    const float ex = pbx - pax, ey = pby - pay, ee = ex * ex + ey * ey;
+    const size_t tile0 = (size_t)view * P.tiles_i * P.tiles_j;
+    for (int t = (int)lane; t < n; t += 32) {
+        const int ti = ti_lo + t / wj, tj = tj_lo + t % wj;
+        if (Rn < 1.0e38f) {  // distance from the tile centre to the projected axis against Rn + the tile's half diagonal
+            const float mx = ((float)(ti * kTileI) + 0.5f * (float)(kTileI - 1)) * pitch - 1.0f - pax;
+            const float my = ((float)(tj * kTileJ) + 0.5f * (float)(kTileJ - 1)) * pitch - 1.0f - pay;
+            const float u = ee > 0.0f ? fminf(fmaxf((mx * ex + my * ey) / ee, 0.0f), 1.0f) : 0.0f;
+            const float qx = mx - u * ex, qy = my - u * ey, lim = Rn + hd;
+            if (qx * qx + qy * qy > lim * lim) continue;
+        }
+        const size_t tile = tile0 + (size_t)ti * P.tiles_j + tj;
+        const unsigned int slot = atomicAdd(counts + tile, 1u);
+        if (slot < cap) lists[tile * cap + slot] = code;
+    }
+}
+
+// d_bins: null, or room for tiles * (1 + bin_cap) words (counts, then lists); n_instances = periods * children of the scene.
 cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count, const unsigned char* d_nfine, const unsigned char* d_section,
-                               unsigned int section_bytes, unsigned int* d_tile_list, unsigned int* d_tile_count, cudaStream_t stream) {
+                               unsigned int section_bytes, unsigned int* d_tile_list, unsigned int* d_tile_count, unsigned int* d_bins,
+                               unsigned int bin_cap, unsigned int n_instances, cudaStream_t stream) {
     const size_t tiles = (size_t)P.n_views * P.tiles_i * P.tiles_j;
     if (tiles == 0) return cudaSuccess;
     if (tiles * 4 > 0xffffffffull) return cudaErrorInvalidValue;
@@ -648,8 +780,19 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    SpanArgs SA = {d_section, section_bytes, d_tile_list, d_tile_count, (unsigned int)(tiles * 4), span_list_cap(section_bytes)};
-    cudaError_t e0 = cudaMemsetAsync(d_tile_count, 0, sizeof(unsigned int), stream);
+    SpanArgs SA = {d_section, section_bytes, d_tile_list, d_tile_count, (unsigned int)(tiles * 4), span_list_cap(section_bytes), nullptr, nullptr, 0u};
+    if (d_bins && bin_cap > 0 && n_instances > 0) {
+        cudaError_t eb = cudaMemsetAsync(d_bins, 0, tiles * sizeof(unsigned int), stream);
+        if (eb != cudaSuccess) return eb;
+        const dim3 bgrid((n_instances + kBlockThreads / 32 - 1) / (kBlockThreads / 32), (unsigned int)P.n_views);
+        span_bin_kernel<<<bgrid, kBlockThreads, 0, stream>>>(P, d_section, d_bins, d_bins + tiles, bin_cap);
+        eb = cudaGetLastError();
+        if (eb != cudaSuccess) return eb;
+        SA.bin_counts = d_bins;
+        SA.bin_lists = d_bins + tiles;
+        SA.bin_cap = bin_cap;
+    }
+    cudaError_t e0 = cudaMemsetAsync(d_tile_count, 0, 2 * sizeof(unsigned int), stream);  // hand-over count, work counter
     if (e0 != cudaSuccess) return e0;
 #define XR_SGO(I, C)                                                                                       \
     do {                                                                                                   \
@@ -660,7 +803,7 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
         int occ = 0;                                                                                       \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem);                \
         if (e != cudaSuccess) return e;                                                                    \
-        const size_t resident = (size_t)sms * (size_t)(occ > 0 ? occ : 1);                                 \
+        const size_t resident = XR_SPAN_PERSISTENT ? (size_t)sms * (size_t)(occ > 0 ? occ : 1) : tiles;    \
         const unsigned int grid = (unsigned int)(tiles < resident ? tiles : resident);                     \
         kern<<<grid, kBlockThreads, smem, stream>>>(P, d_nfine, SA);                                       \
         return cudaGetLastError();                                                                         \

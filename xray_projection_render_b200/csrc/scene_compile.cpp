@@ -1502,10 +1502,14 @@ static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
         H.uc_hi[a] = hi[a];
         cmax = std::fmax(cmax, std::fmax(std::fabs(H.outer[a]), std::fabs(H.outer[3 + a])) + std::fabs(lo[a]) + ext[a]);
     }
-    if (tess)  // number of periods a ray can cross stays small enough for the 4-bit period codes of the kernel
+    H.n_periods = 1;
+    if (tess)  // number of periods a ray can cross stays small enough for the 5-bit period codes of the kernel
         for (int a = 0; a < 3; ++a) {
             const double n_lo = std::floor((H.outer[a] - lo[a]) / ext[a]), n_hi = std::floor((H.outer[3 + a] - lo[a]) / ext[a]);
             if (!(n_lo >= -14.0 && n_hi <= 14.0)) return false;  // one period of slack: the walk starts a hair outside the box
+            H.n_lo[a] = (int32_t)n_lo;
+            H.n_hi[a] = (int32_t)n_hi;
+            H.n_periods *= (uint32_t)(H.n_hi[a] - H.n_lo[a] + 1);
         }
     for (const Node* k : kids) switch (k->type) {
             case N_SPHERE: feat = std::fmin(feat, std::fabs(k->p[3])); break;
@@ -1562,11 +1566,19 @@ static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
                 for (int i = 0; i < 3; ++i) r.p[i] = p[i], r.f[i] = (float)p[i];
                 r.p[3] = p[3] * p[3];  // objects.go:67: dist2 < Radius*Radius
                 r.f[3] = (float)((std::fabs(p[3]) + fm) * (std::fabs(p[3]) + fm));
+                for (int i = 0; i < 3; ++i) r.bs[i] = (float)p[i];
+                r.bs[3] = (float)(std::fabs(p[3]) + fm);
                 break;
             case N_BOX:
                 r.type = OP_BOX;
                 r.rho = p[6];
                 for (int i = 0; i < 3; ++i) r.p[i] = p[i], r.p[3 + i] = 0.5 * p[3 + i];  // objects.go:175: 0.5*Sides[i]
+                {
+                    const double R = 0.5 * std::sqrt(p[3] * p[3] + p[4] * p[4] + p[5] * p[5]) + fm;
+                    for (int i = 0; i < 3; ++i) r.bs[i] = r.f[i] = (float)p[i];
+                    r.bs[3] = (float)R;
+                    r.f[3] = (float)(R * R);
+                }
                 break;
             case N_CYL: {
                 r.type = OP_CYL;
@@ -1582,6 +1594,7 @@ static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
                 r.f[6] = (float)(1.0 / vv);
                 r.f[7] = (float)((std::fabs(p[6]) + fm) * (std::fabs(p[6]) + fm));
                 if (p[6] < 0) return false;  // d < r never holds: leave such scenes to the point evaluators
+                r.bs[3] = (float)(std::fabs(p[6]) + fm);  // capsule radius around the axis p0 .. p0 + v (f[0..5])
                 break;
             }
             default: {
@@ -1595,6 +1608,23 @@ static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
                     r.p[3 + 3 * i + 2] = m[6 + i];
                     r.p[12 + i] = std::fabs(m[i]) + std::fabs(m[3 + i]) + std::fabs(m[6 + i]);
                     if (!std::isfinite(r.p[12 + i])) return false;
+                }
+                {  // bounding sphere about the centre o + (v0 + v1 + v2) / 2
+                    double c[3], R = 0;
+                    for (int i = 0; i < 3; ++i) c[i] = p[i] + 0.5 * (p[3 + i] + p[6 + i] + p[9 + i]);
+                    for (int m8 = 0; m8 < 8; ++m8) {
+                        double q[3], d2 = 0;
+                        for (int i = 0; i < 3; ++i) {
+                            q[i] = p[i] + ((m8 & 1) ? p[3 + i] : 0) + ((m8 & 2) ? p[6 + i] : 0) + ((m8 & 4) ? p[9 + i] : 0);
+                            d2 += (q[i] - c[i]) * (q[i] - c[i]);
+                        }
+                        R = std::fmax(R, std::sqrt(d2));
+                    }
+                    R += fm;
+                    if (!std::isfinite(R)) return false;
+                    for (int i = 0; i < 3; ++i) r.bs[i] = r.f[i] = (float)c[i];
+                    r.bs[3] = (float)R;
+                    r.f[3] = (float)(R * R);
                 }
                 break;
             }
