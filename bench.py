@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the per-pixel projection hot path.
 
-python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--no-configs]
 
-A "step" is one pass of the hot path over one batch: all views of the workload (per rank).
-Default workload = BASELINE.json configs[1]: tests/scenes/lattice.json (= examples/lattice.yaml),
+A "step" is one pass of the hot path over one batch: all views of the workload.
+Headline workload = BASELINE.json configs[1]: tests/scenes/lattice.json (= examples/lattice.yaml),
 360 views at 1024x1024, hierarchical integrator, auto ds, R=4, fov=40, polar=90, fp32 mode.
-N>1 (torchrun, one rank per GPU): weak scaling -- the global view list has N*views equispaced
-azimuths, rank r renders views r, r+N, ... (the reference's --jobs_modulo/--job sharding); no
-data-path collective.  Prints ONE JSON line on rank 0.
+The same JSON line carries the other BASELINE configs as sub-records under "configs" (cfg1 in full; cfg3, cfg4, cfg5 on
+a bounded number of their views, stated), each with its device-resident value, end-to-end value, roofline and an in-run
+parity spot check against the oracle.
+N>1 (torchrun, one rank per GPU): STRONG scaling of the fixed configs -- rank r renders views r, r+N, ... of the same
+view list (the reference's --jobs_modulo/--job sharding, main.go:244); analytic scenes need no data-path collective; the
+voxel config uploads the volume on rank 0 only and replicates it with one NCCL broadcast INSIDE the timed end-to-end
+region.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -76,33 +80,6 @@ def scene_flops_model(obj: dict, deform: dict | None):
 
     walk(obj)
     return per_sample, (sum(prim) / len(prim) if prim else 0.0), float(sum(prim))
-
-
-def inbounds_samples(cams, res, lo, hi, ds, sub=128):
-    """Reference-equivalent coarse samples that fall inside the scene's bounding box (where the Go path does its
-    arithmetic: everything outside returns from a bounds test), summed over the views: slab clipping of every ray of a
-    sub x sub pixel subsample, scaled to res x res.  Used only for the SURVEY 8(d) brute-force flop figure."""
-    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
-    if not (np.isfinite(lo).all() and np.isfinite(hi).all()):
-        lo, hi = np.maximum(lo, -1.74), np.minimum(hi, 1.74)
-    sub = min(sub, res)
-    px = (np.arange(sub) * (res // sub)) / (res / 2.0) - 1.0
-    gi, gj = np.meshgrid(px, px, indexing="ij")
-    total = 0.0
-    for c in cams:
-        eye = np.array(list(c.eye))
-        m = np.array(list(c.view)).reshape(4, 4)
-        f = 1.0 / np.tan(np.radians(c.fov_y) / 2.0)
-        v = np.stack([gi, gj, np.full_like(gi, -f), np.ones_like(gi)], -1) @ m.T
-        d = v[..., :3] / v[..., 3:4] - eye
-        d /= np.linalg.norm(d, axis=-1, keepdims=True)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            a0, a1 = (lo - eye) / d, (hi - eye) / d
-        t0 = np.nanmax(np.minimum(a0, a1), axis=-1)
-        t1 = np.nanmin(np.maximum(a0, a1), axis=-1)
-        t0, t1 = np.maximum(t0, c.R - 1.74), np.minimum(t1, c.R + 1.74)
-        total += float(np.maximum(t1 - t0, 0.0).sum()) / ds
-    return total * (res / sub) ** 2
 
 
 class ClockSampler:
@@ -176,16 +153,29 @@ def rank_views(total_views: int, rank: int, world: int):
 
 
 # ----------------------------------------------------------------------------------------
+# Workload description shared by both arms (so that the driver sees the same `config.workload`)
+# ----------------------------------------------------------------------------------------
+def workload_string(name: str, volume_n: int = 1024) -> str:
+    obj, deform, views, res, integ, ds = WORKLOADS[name]
+    scene = obj if obj else f"synthetic {volume_n}^3 fp32 volume"
+    if deform:
+        scene += " + " + deform
+    return f"{name}: {scene}, {views} views at {res}x{res}, {integ}, auto ds, R={R_CAM}, fov={FOV}, polar={POLAR}"
+
+
+# ----------------------------------------------------------------------------------------
 # CPU baseline (oracle = C++ restatement of the Go path; kind "port")
 # ----------------------------------------------------------------------------------------
-def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
+def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0, volume=None):
+    """The reference's CPU path (oracle/xray_oracle.cpp, all host threads) on a bounded sample of the workload's rays,
+    sized for ~budget_s of wall time after a short calibration."""
     from oracle import oracle as O
 
     obj, deform, views, res, integ, ds = WORKLOADS[workload]
     if obj is None:
-        n = 256
-        vol = synthetic_volume(n)
-        osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)})
+        if volume is None:
+            volume = synthetic_volume(256)
+        osc = O.OracleScene({"type": "voxel_grid", "_array_f32": np.ascontiguousarray(volume, dtype=np.float32)})
         ds_v = 2.0 / 1024 / 5.0  # the full-size workload's step: same per-sample cost model
         sample_res = 64
     else:
@@ -195,13 +185,19 @@ def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
     # all host cores this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for every rank
     threads = nthreads or max(O.max_threads(), len(os.sched_getaffinity(0)))
     angles = O.generate_camera_angles(views)
-    # calibrate on a thin strip, then size the sample for ~budget_s of CPU work
+    # calibrate on a strip that takes a good fraction of a second, then size the sample for ~budget_s of CPU work
     eye, cm = O.camera_from_angles(*angles[0], R_CAM)
     mid = sample_res // 2
-    t0 = time.perf_counter()
-    _, n0 = osc.render_view(eye, cm, sample_res, FOV, R_CAM, ds_v, integ, rows=(mid, mid + max(1, threads // 4)), nthreads=threads)
-    dt0 = max(time.perf_counter() - t0, 1e-4)
-    rows_per_s = max(1, threads // 4) / dt0
+    rows0 = max(1, threads // 4)
+    while True:
+        t0 = time.perf_counter()
+        osc.render_view(eye, cm, sample_res, FOV, R_CAM, ds_v, integ, rows=(max(0, mid - rows0 // 2), min(sample_res, mid - rows0 // 2 + rows0)),
+                        nthreads=threads)
+        dt0 = max(time.perf_counter() - t0, 1e-4)
+        if dt0 > 0.25 or rows0 >= sample_res:
+            break
+        rows0 = min(sample_res, rows0 * 4)
+    rows_per_s = rows0 / dt0
     want_rows = int(min(64 * sample_res, max(threads, rows_per_s * budget_s)))
     n_views = max(1, min(64, -(-want_rows // sample_res)))
     rows_each = max(1, min(sample_res, want_rows // n_views))
@@ -221,7 +217,7 @@ def cpu_baseline(workload: str, budget_s: float = 15.0, nthreads: int = 0):
             "sample": desc, "seconds": dt}
 
 
-def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, device_index):
+def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step):
     """Second comparator of BASELINE.md: the reference's own CUDA plugin (cuda_backend.cu built unmodified for
     sm_100 into oracle/_ref/ by oracle/Makefile), driven through the same legacy call with the same host
     buffers.  Speed only: its images follow the half-voxel texture convention (cuda_test.go:33-40)."""
@@ -237,8 +233,7 @@ def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, d
                                                     ctypes.c_float, ctypes.c_float, fp]
         cams32 = X.to_legacy(cams)
         n = len(cams32)
-        vol_np = np.array(vol_np, copy=True)  # pageable, like the Go heap buffer the host hands over (cuda_backend.go:316)
-        nz, nx, ny = vol_np.shape
+        nz, nx, ny = vol_np.shape  # pageable, like the Go heap buffer the host hands over (cuda_backend.go:316)
         out = np.empty((n, res, res), dtype=np.float32)
         ours = np.empty((n, res, res), dtype=np.float32)
         args = (vol_np.ctypes.data_as(fp), nx, ny, nz, cams32, n, res, ctypes.c_float(ds), ctypes.c_float(0.0))
@@ -253,7 +248,7 @@ def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, d
         X.render_volume_legacy(vol_np, cams32, res, float(np.float32(ds)), out=ours)
         t_ours = time.perf_counter() - t0
         return {"what": "reference cuda_backend.cu (sm_100 build) vs this library, same RenderVolumeProjectionsCUDA call, same pageable host buffers (as the Go host passes)",
-                "reference_s": t_ref, "ours_s": t_ours, "reference_gsamples_per_s": ref_samples_per_step / t_ref / 1e9,
+                "views": n, "reference_s": t_ref, "ours_s": t_ours, "reference_gsamples_per_s": ref_samples_per_step / t_ref / 1e9,
                 "ours_gsamples_per_s": ref_samples_per_step / t_ours / 1e9, "speedup": t_ref / t_ours,
                 "max_abs_image_diff": float(np.abs(out - ours).max()),
                 "note": "image difference is the reference kernel's half-voxel texture convention, not an error of either"}
@@ -263,28 +258,34 @@ def time_reference_cuda_plugin(X, vol_np, cams, res, ds, ref_samples_per_step, d
 
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU implementation of the path (C++ restatement of the Go
-    code, all host threads) on the same workload/metric.  Rank 0 only."""
+    code, all host threads) on the same workload/metric.  Rank 0 only.  Every step is a bounded sample of at least
+    3 s of wall time (short samples were dominated by thread start-up), so the step count is capped at 5."""
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    vals = []
+    steps = max(1, min(args.steps, 5))
+    per_step = max(3.0, args.cpu_budget / steps)
+    vol = synthetic_volume(256) if WORKLOADS[args.workload][0] is None else None
     for _ in range(max(0, min(args.warmup, 1))):
-        cpu_baseline(args.workload, budget_s=2.0)
+        cpu_baseline(args.workload, budget_s=1.0, volume=vol)
+    vals = []
     t_all = time.perf_counter()
     for _ in range(steps):
-        vals.append(cpu_baseline(args.workload, budget_s=args.cpu_budget / steps))
+        vals.append(cpu_baseline(args.workload, budget_s=per_step, volume=vol))
     wall = time.perf_counter() - t_all
-    v = float(np.mean([x["gsamples_per_s"] for x in vals]))
-    rays = float(np.mean([x["rays_per_s"] for x in vals]))
-    obj, deform, views, res, integ, ds = WORKLOADS[args.workload]
+    samples = sum(x["gsamples_per_s"] * x["seconds"] for x in vals)
+    secs = sum(x["seconds"] for x in vals)
+    v = samples / secs
+    rays = sum(x["rays_per_s"] * x["seconds"] for x in vals) / secs
     line = {
         "impl": "reference", "metric": "Gsamples/s", "value": v, "unit": "Gsamples/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "projections_512_per_s": rays / 262144.0,
-        "config": {"workload": f"{args.workload}: {obj or 'synthetic 1024^3 volume'}, {views} views at {res}x{res}, {integ}, "
-                               f"R={R_CAM}, fov={FOV}, polar={POLAR}", "note": "CPU path timed on a bounded sample (see cpu_baseline.sample)"},
-        "cpu_baseline": {"value": v, "unit": "Gsamples/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+        "config": {"workload": workload_string(args.workload, args.volume_n),
+                   "note": "CPU path timed on a bounded sample of the workload's rays (see cpu_baseline.sample); the rate is per sample, "
+                           "so it does not depend on how many GPUs the other arm uses"},
+        "cpu_baseline": {"value": v, "unit": "Gsamples/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"],
+                         "per_step_values": [x["gsamples_per_s"] for x in vals]},
         "e2e": {"value": v, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -293,6 +294,239 @@ def run_reference(args, rank: int, world: int):
 # ----------------------------------------------------------------------------------------
 # Our arm
 # ----------------------------------------------------------------------------------------
+# Algorithmic work of the interval renderer (render_span.cu), fp32-equivalent flops (an fp64 operation counted as 2):
+# per candidate that reaches the exact stage: 3 period slabs + cap slab + quadratic + two ordinal look-ups ~ 110 fp64 ops;
+# per ray: ray set-up, outer-box clip, sweep ~ 90 fp64 ops + 40 fp32.
+FLOPS_SPAN_CANDIDATE = 220
+FLOPS_SPAN_RAY = 220
+STAT_KEYS = ("ref_samples", "evaluated_samples", "fp64_fallbacks", "primitive_tests", "rays", "launches", "marched_tiles")
+
+
+def measure(X, torch, dist, name, rank, world, local_rank, steps, warmup, flush, views_total=0, volume_n=1024, volume=None,
+            parity=True, ref_cuda=False, sampler=None, ncu_info=None):
+    """Time one workload on this process group: device-resident value, end-to-end value (pageable and pinned host buffers),
+    roofline, parity spot check.  Returns the record on rank 0, None elsewhere."""
+    dev = torch.device("cuda", local_rank)
+    obj, deform, views_full, res, integ, ds = WORKLOADS[name]
+    views_total = views_total or views_full
+    angles = rank_views(views_total, rank, world)  # strong scaling: this rank's share of the fixed view list
+    cams = X.cameras_from_angles(angles, R_CAM, FOV)
+    n = len(cams)
+    stream = torch.cuda.current_stream()
+    out_dev = torch.empty((max(n, 1), res, res), dtype=torch.float32, device=dev)
+    out_page = np.empty((max(n, 1), res, res), dtype=np.float32)            # pageable: what a Go / numpy caller hands over
+    out_pin = torch.empty((max(n, 1), res, res), dtype=torch.float32, pin_memory=True)
+    stats = (ctypes.c_uint64 * X._lib.XRAY_NUM_STATS)()
+    is_volume = obj is None
+    bcast_ms = []
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if is_volume:
+        nvox = volume_n
+        if rank == 0 and volume is None:
+            volume = synthetic_volume(nvox)
+        vol_np = volume if rank == 0 else None   # pageable numpy array on rank 0 only
+        vol_pin = torch.from_numpy(vol_np).pin_memory() if rank == 0 else None
+        vol_dev = torch.empty((nvox, nvox, nvox), dtype=torch.float32, device=dev)
+        if rank == 0:
+            vol_dev.copy_(vol_pin, non_blocking=True)
+        if dist is not None:
+            dist.broadcast(vol_dev, src=0)
+        ds_v = 2.0 / nvox / 5.0
+        scene = None
+
+        def step_device(st=None):
+            if n:
+                X.render_volume_device(vol_dev, (nvox, nvox, nvox), cams, res, out_dev, ds=ds_v, stream=stream.cuda_stream, stats=st)
+
+        if world == 1:
+            def step_e2e(host_out):  # the call the Go host makes, volume re-uploaded from host memory every call
+                X.render_volume(vol_np, cams, res, ds=ds_v, out=host_out)
+            h2d_step = vol_dev.numel() * 4
+            e2e_api = "XRayRenderVolumeExCUDA"
+        else:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            host_t = {}
+
+            def step_e2e(host_out):
+                # rank 0 uploads the volume ONCE, one NCCL broadcast over NVLink replicates it, every rank renders its views
+                # from the device copy and returns its images to host memory
+                if rank == 0:
+                    vol_dev.copy_(vol_pin, non_blocking=True)
+                ev0.record(stream)
+                dist.broadcast(vol_dev, src=0)
+                ev1.record(stream)
+                if n:
+                    X.render_volume_device(vol_dev, (nvox, nvox, nvox), cams, res, out_dev, ds=ds_v, stream=stream.cuda_stream)
+                    key = host_out.ctypes.data
+                    if key not in host_t:
+                        host_t[key] = torch.from_numpy(host_out)
+                    host_t[key].copy_(out_dev[:n], non_blocking=False)
+                torch.cuda.synchronize()
+                bcast_ms.append(ev0.elapsed_time(ev1))
+            h2d_step = vol_dev.numel() * 4 if rank == 0 else 0
+            e2e_api = "pinned H2D on rank 0 + ncclBroadcast + XRayRenderVolumeDeviceCUDA + D2H"
+    else:
+        scene = X.Scene(str(SCENES / obj), str(SCENES / deform) if deform else None)
+        ds_v = scene.auto_ds() if ds <= 0 else ds
+
+        def step_device(st=None):
+            if n:
+                X.render_scene_device(scene, cams, res, out_dev, integration=integ, precision="fp32", ds=ds_v,
+                                      stream=stream.cuda_stream, stats=st)
+
+        def step_e2e(host_out):
+            if n:
+                X.render_scene(scene, cams, res, integration=integ, precision="fp32", ds=ds_v, out=host_out)
+
+        h2d_step = len(scene.program_bytes()) + n * ctypes.sizeof(X._lib.XRayCameraParams64) + 12 * int(3.48 / ds_v + 2)
+        e2e_api = "XRayRenderSceneCUDA"
+
+    # ---- kernel-resident arm: inputs (program / volume) already in HBM, output stays in HBM ----
+    # work counters come from ONE untimed pass of the counting kernel variants; the timed passes run the production variants
+    step_device(stats)
+    st1 = {k: int(stats[i]) for i, k in enumerate(STAT_KEYS)}
+    span_ran = bool(int(stats[7]) & 0x10000)
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(steps):
+        flush.fill_(k & 0xFF)  # evict the previous step's lines from L2 (not timed)
+        evs[k][0].record(stream)
+        step_device()
+        evs[k][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler is not None else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- end-to-end arm: public host API, HOST buffers, H2D + D2H inside the timed region ----
+    def time_e2e(host_out):
+        for _ in range(min(warmup, 2)):
+            step_e2e(host_out)
+        bcast_ms.clear()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e(host_out)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_page_s = time_e2e(out_page[:max(n, 1)])
+    bcast_page = list(bcast_ms)
+    e2e_pin_s = time_e2e(out_pin.numpy()[:max(n, 1)])
+
+    # ---- parity spot check (rank 0): 256 random pixels of this rank's first view against the oracle ----
+    spot = None
+    if parity and rank == 0 and n:
+        from oracle import oracle as O
+
+        rng = np.random.default_rng(2024)
+        ij = np.stack([rng.integers(0, res, 256), rng.integers(0, res, 256)], axis=1).astype(np.int32)
+        if is_volume:
+            osc = O.OracleScene({"type": "voxel_grid", "_array_f32": vol_np})
+        else:
+            osc = O.OracleScene(str(SCENES / obj), str(SCENES / deform) if deform else None)
+        c0 = cams[0]
+        want, _ = osc.render_pixels(np.array(list(c0.eye)), np.array(list(c0.view)).reshape(4, 4), res, float(c0.fov_y), float(c0.R),
+                                    ds_v, ij, integ)
+        got = out_page[0][ij[:, 0], ij[:, 1]].astype(np.float64)
+        spot = {"max_abs_dI": float(np.abs(got - want).max()), "pixels": 256, "view": [float(angles[0]["azimuthal"]), float(angles[0]["polar"])],
+                "tolerance": 1e-4, "against": "oracle (C++ restatement of the Go CPU path), same camera and step",
+                "attenuated_pixels": int((want < 0.999).sum())}
+
+    # ---- reduce over ranks: max time, sum of work ----
+    vec = torch.tensor([dev_ms, e2e_page_s * 1e3, e2e_pin_s * 1e3, float(np.mean(bcast_page)) if bcast_page else 0.0], dtype=torch.float64, device=dev)
+    work = torch.tensor([st1[k] for k in STAT_KEYS] + [float(h2d_step), float(n * res * res * 4)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_page_ms, e2e_pin_ms, bcast_mean = (float(x) for x in vec.tolist())
+    w = dict(zip(STAT_KEYS + ("h2d", "d2h"), (float(x) for x in work.tolist())))
+    if rank != 0:
+        return None
+
+    secs = dev_ms_max / 1e3 / steps            # per step, max over ranks
+    ref_samples, rays = w["ref_samples"], w["rays"]   # per step, all ranks
+    rec = {
+        "workload": workload_string(name, volume_n), "views_rendered": views_total, "views_in_config": views_full,
+        "value": ref_samples / secs / 1e9, "unit": "Gsamples/s", "ms_per_step": dev_ms_max / steps,
+        "projections_512_per_s": rays / secs / 262144.0, "rays_per_s": rays / secs,
+        "e2e": {"value": ref_samples / (e2e_page_ms / 1e3 / steps) / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": int(w["h2d"]),
+                "d2h_bytes_per_step": int(w["d2h"]), "ms_per_step": e2e_page_ms / steps, "host_buffers": "pageable (numpy), as a cgo / ctypes caller passes",
+                "pinned": {"value": ref_samples / (e2e_pin_ms / 1e3 / steps) / 1e9, "ms_per_step": e2e_pin_ms / steps},
+                "projections_512_per_s": rays / (e2e_page_ms / 1e3 / steps) / 262144.0, "api": e2e_api},
+        "gpu_launches": int(w["launches"]) * steps, "launches_per_step": int(w["launches"]),
+        "parity_spot_check": spot, "wall_s_timed_region": t_wall, "clocks": clocks,
+        "work_per_step": {"ref_samples": ref_samples, "rays": rays, "intervals_or_evaluated_samples": w["evaluated_samples"],
+                          "candidate_or_primitive_tests": w["primitive_tests"], "fp64_fallbacks": w["fp64_fallbacks"],
+                          "warp_tiles_handed_to_marching_kernels": w["marched_tiles"]},
+    }
+    if world > 1 and is_volume:
+        rec["e2e"]["broadcast_ms"] = bcast_mean
+    # ---- roofline of the dominant kernel ----
+    launches = max(1.0, w["launches"] / world)   # per rank and step
+    peak_tflops = X.measure_fp32_peak()
+    if is_volume:
+        # voxel kernel: bound by the memory hierarchy.  Algorithmic (compulsory) bytes per view: the volume read once
+        # (4 N^3) plus the image written once (4 res^2) -- SURVEY 8(d); peak = measured HBM copy bandwidth.
+        peaks = {}
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        except (OSError, ValueError):
+            pass
+        hbm = float(peaks.get("hbm_gbs", 6491.2))
+        bytes_view = 4.0 * volume_n ** 3 + 4.0 * res * res
+        ach = bytes_view * views_total / world / secs / 1e9   # per GPU
+        rec["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "B200_PROFILING.md fallback",
+                           "algorithmic_bytes_per_launch": bytes_view * views_total / world / launches,
+                           "avg_launch_ms": dev_ms_max / steps / launches,
+                           "note": "compulsory bytes: volume once + image once per view; the trilinear tap stream itself is served on chip"}
+    else:
+        if span_ran:
+            flops = w["primitive_tests"] * FLOPS_SPAN_CANDIDATE + rays * FLOPS_SPAN_RAY
+            model = {"per_exact_interval_candidate": FLOPS_SPAN_CANDIDATE, "per_ray": FLOPS_SPAN_RAY, "kernel": "render_span_kernel"}
+        else:
+            per_sample, per_prim, _ = scene_flops_model(scene.object_map, scene.deformation_map)
+            flops = w["evaluated_samples"] * per_sample + w["primitive_tests"] * per_prim
+            model = {"per_evaluated_sample": per_sample, "per_primitive_test": per_prim, "kernel": "marching kernels"}
+        ach = flops / world / secs / 1e12
+        rec["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops if peak_tflops else None,
+                           "traffic": None, "peak_source": "measured in this run: FFMA-chain microbenchmark (XRayMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
+                           "algorithmic_flops_per_launch": flops / world / launches, "avg_launch_ms": dev_ms_max / steps / launches,
+                           "flops_model": model,
+                           "note": "the executed algorithm removes the per-sample flops the reference spends (intervals instead of samples), so the "
+                                   "fraction of the FP32 peak is small by construction; the binding resource is warp-instruction issue (see issue)"}
+    if ncu_info and name in ncu_info:
+        tr = ncu_info[name]
+        vps = views_total / world   # views per rank and step
+        rec["roofline"]["traffic"] = tr["dram_bytes_per_view"] * vps / launches
+        rec["roofline"]["traffic_source"] = tr["capture"]
+        if clocks and clocks.get("sm_mhz") and tr.get("warp_inst_per_view"):
+            inst_s = tr["warp_inst_per_view"] * vps / secs
+            peak_inst = 4.0 * 148 * clocks["sm_mhz"] * 1e6
+            rec["roofline"]["issue"] = {"warp_inst_per_view": tr["warp_inst_per_view"], "warp_inst_per_ray": tr["warp_inst_per_view"] / (res * res),
+                                        "achieved_ginst_per_s": inst_s / 1e9, "peak_ginst_per_s": peak_inst / 1e9, "frac": inst_s / peak_inst,
+                                        "note": "instruction count from the committed ncu capture of this kernel, time from this run"}
+    if is_volume and world == 1 and ref_cuda:
+        rec["reference_cuda"] = time_reference_cuda_plugin(X, vol_np, cams, res, ds_v, ref_samples)
+    return rec
+
+
+SUB_CONFIGS = (  # (key, workload, views rendered on N = 1)
+    ("cfg1", "cube_w_hole", 1), ("cfg3", "gyroid_sigmoid", 90), ("cfg4", "voxel1024", 16), ("cfg5", "pillar_array", 8))
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
 
@@ -308,185 +542,60 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-
-    obj, deform, views, res, integ, ds = WORKLOADS[args.workload]
-    if args.views:
-        views = args.views
-    if args.res:
-        res = args.res
-    if args.integ:
-        integ = args.integ
-    angles = rank_views(views * world, rank, world)
-    cams = X.cameras_from_angles(angles, R_CAM, FOV)
-    n = len(cams)
-    stream = torch.cuda.current_stream()
-    out_dev = torch.empty((n, res, res), dtype=torch.float32, device=dev)
-    out_host = torch.empty((n, res, res), dtype=torch.float32, pin_memory=True)
-    stats = (ctypes.c_uint64 * X._lib.XRAY_NUM_STATS)()
-
-    is_volume = obj is None
-    if is_volume:
-        nvox = args.volume_n
-        vol_host = torch.from_numpy(synthetic_volume(nvox)).pin_memory() if rank == 0 else None
-        vol_dev = torch.empty((nvox, nvox, nvox), dtype=torch.float32, device=dev)
-        if rank == 0:
-            vol_dev.copy_(vol_host, non_blocking=True)
-        if dist is not None:
-            dist.broadcast(vol_dev, src=0)  # the only collective: replicate the volume over NVLink
-        ds_v = 2.0 / nvox / 5.0
-        h2d = vol_dev.numel() * 4 if rank == 0 else 0
-
-        def step_device(st=None):
-            X.render_volume_device(vol_dev, (nvox, nvox, nvox), cams, res, out_dev, ds=ds_v, stream=stream.cuda_stream, stats=st)
-
-        vol_np = vol_host.numpy() if rank == 0 else synthetic_volume(nvox)
-
-        def step_e2e():
-            X.render_volume(vol_np, cams, res, ds=ds_v, out=out_host.numpy())
-
-        per_sample, per_prim, brute_prims = 3 + 6, 14 + 2, 0.0
-        scene = None
-        h2d_step = vol_dev.numel() * 4
-    else:
-        scene = X.Scene(str(SCENES / obj), str(SCENES / deform) if deform else None)
-        ds_v = scene.auto_ds() if ds <= 0 else ds
-        per_sample, per_prim, brute_prims = scene_flops_model(scene.object_map, scene.deformation_map)
-
-        def step_device(st=None):
-            X.render_scene_device(scene, cams, res, out_dev, integration=integ, precision="fp32", ds=ds_v,
-                                  stream=stream.cuda_stream, stats=st)
-
-        def step_e2e():
-            X.render_scene(scene, cams, res, integration=integ, precision="fp32", ds=ds_v, out=out_host.numpy())
-
-        h2d_step = len(scene.program_bytes()) + n * ctypes.sizeof(X._lib.XRayCameraParams64) + 12 * int(3.48 / ds_v + 2)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    peak_tflops = X.measure_fp32_peak()
+    try:
+        ncu_info = json.load(open(ROOT / "profiles" / "ncu_dram_traffic_r2.json"))
+    except (OSError, ValueError):
+        ncu_info = None
 
-    # ---- kernel-resident arm: inputs (program / volume) already in HBM, output stays in HBM ----
-    # work counters come from ONE untimed pass of the counting kernel variant; the timed passes
-    # run the production variant (no counters)
-    step_device(stats)
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)  # evict the previous step's lines from L2 (not timed)
-        evs[k][0].record(stream)
-        step_device()
-        evs[k][1].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    st = {k: int(stats[i]) * args.steps for i, k in enumerate(("ref_samples", "evaluated_samples", "fp64_fallbacks", "primitive_tests", "rays", "launches"))}
-
-    # ---- end-to-end arm: public host API, host buffers, H2D + D2H inside the timed region ----
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-
-    # ---- reduce over ranks: max time, sum of work ----
-    vec = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    work = torch.tensor([st["ref_samples"], st["rays"], st["evaluated_samples"], st["primitive_tests"], st["launches"],
-                         st["fp64_fallbacks"]], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = (float(x) for x in vec.tolist())
-    ref_samples, rays, evaluated, prim_tests, launches, fallbacks = (float(x) for x in work.tolist())
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    is_volume = WORKLOADS[args.workload][0] is None
+    volume = synthetic_volume(args.volume_n) if (rank == 0 and (is_volume or not args.no_configs)) else None
+    main = measure(X, torch, dist, args.workload, rank, world, local_rank, args.steps, args.warmup, flush, views_total=args.views,
+                   volume_n=args.volume_n, volume=volume if is_volume else None, sampler=sampler, ncu_info=ncu_info,
+                   ref_cuda=not args.no_ref_cuda)
+    subs = {}
+    if not args.no_configs:
+        for key, name, nv in SUB_CONFIGS:
+            if name == args.workload or (world > 1 and key == "cfg1"):
+                continue
+            nv_total = nv * world if world > 1 else nv   # every rank keeps the same bounded share of the config's view list
+            r = measure(X, torch, dist, name, rank, world, local_rank, 2, 3, flush, views_total=nv_total, volume_n=args.volume_n,
+                        volume=volume if name == "voxel1024" else None, ncu_info=ncu_info, ref_cuda=(world == 1 and not args.no_ref_cuda))
+            if rank == 0:
+                subs[key] = r
     if dist is not None:
         dist.destroy_process_group()
     if rank != 0:
         return
-
-    secs = dev_ms_max / 1e3
-    gsamples = ref_samples / secs / 1e9
-    rays_s = rays / secs
-    e2e_secs = e2e_ms_max / 1e3
-    e2e_gs = ref_samples / e2e_secs / 1e9
-    # roofline of the dominant (only) kernel in the timed region
-    alg_flops = evaluated * per_sample + prim_tests * per_prim  # all ranks, all steps
-    kernel_ms = dev_ms_max / max(1.0, launches / world) if launches else dev_ms_max
-    achieved = alg_flops / world / secs / 1e12  # per GPU TFLOP/s
-    roof = {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
-            "traffic": None, "peak_source": "measured in this run: FFMA-chain microbenchmark (XRayMeasureFp32Peak); MEASURED_PEAKS.json has no FP32 figure",
-            "algorithmic_flops_per_launch": alg_flops / max(1.0, launches), "avg_launch_ms": kernel_ms,
-            "flops_model": {"per_evaluated_sample": per_sample, "per_primitive_test": per_prim},
-            "evaluated_samples": evaluated, "primitive_tests": prim_tests, "fp64_fallbacks": fallbacks}
-    if not is_volume:
-        # SURVEY.md 8(d) as written: algorithmic flops of the reference's own algorithm (every child of the collection
-        # tested at every sample inside the scene bounds, nothing outside) for the samples this run covered.  The kernel
-        # does not execute these flops -- culling and exact skipping remove most of them -- so this "fraction" states how
-        # far the run is ahead of an fp32 brute-force evaluator running AT the FP32 roofline, and may exceed 1.
-        lo, hi = scene.bounds()
-        inb = inbounds_samples(cams, res, lo, hi, ds_v) * args.steps  # this rank; ranks are symmetric under weak scaling
-        brute = per_sample + brute_prims
-        roof["survey_8d_brute_force"] = {
-            "flops_per_inbounds_sample": brute, "inbounds_samples": inb * world,
-            "achieved": inb * brute / secs / 1e12, "unit": "TFLOP/s (reference-algorithm flops / GPU)",
-            "frac": inb * brute / secs / 1e12 / peak_tflops if peak_tflops else None,
-            "note": "flops the reference's brute-force density() spends on these samples, not flops executed here"}
-    try:  # DRAM traffic of this kernel per launch, from the committed ncu capture of the same workload
-        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_dram_traffic_r1.json")))[args.workload]
-        roof["traffic"] = tr["dram_bytes_per_view"] * (views * world * args.steps / max(1.0, launches))
-        roof["traffic_source"] = tr["capture"] + " (per view) x views per launch"
-        if clocks and clocks.get("sm_mhz") and tr.get("warp_inst_per_view"):
-            # what actually binds these kernels: warp-instruction issue slots (4 schedulers x 148 SMs x SM clock)
-            inst_s = tr["warp_inst_per_view"] * views * args.steps / secs
-            peak_inst = 4.0 * 148 * clocks["sm_mhz"] * 1e6
-            roof["issue"] = {"warp_inst_per_view": tr["warp_inst_per_view"], "achieved_ginst_per_s": inst_s / 1e9,
-                             "peak_ginst_per_s": peak_inst / 1e9, "frac": inst_s / peak_inst,
-                             "note": "instruction count from the committed ncu capture, time from this run"}
-    except (OSError, KeyError, ValueError):
-        pass
-    if is_volume:
-        tap_bytes = evaluated * 32.0
-        roof.update({"bound": "l1", "achieved": tap_bytes / world / secs / 1e9, "unit": "GB/s",
-                     "peak": 128.0 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None})
-        roof["frac"] = roof["achieved"] / roof["peak"] if roof["peak"] else None
-        roof["peak_source"] = ("L1/shared 128 B/clk/SM x 148 SM x measured SM clock (tap stream is served on chip, HBM is <5% utilised); "
-                               "the unit that saturates first is texture write-back (ncu: l1tex__tex_writeback_active 89 %)")
+    obj, deform, views, res, integ, ds = WORKLOADS[args.workload]
     line = {
-        "metric": "Gsamples/s", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "projections_512_per_s": rays_s / 262144.0, "rays_per_s": rays_s,
-        "config": {"workload": f"{args.workload}: {obj or f'synthetic {args.volume_n}^3 fp32 volume'}, {views} views/GPU at {res}x{res}, "
-                               f"{integ}, ds={ds_v:.6g}, R={R_CAM}, fov={FOV}, polar={POLAR}, fp32 guard-banded mode",
-                   "views_total": views * world, "sharding": "views modulo rank (independent, no data-path collective)",
-                   "l2": "256 MiB buffer rewritten between timed steps; output (>=1.5 GB) exceeds the 126 MB L2"},
-        "e2e": {"value": e2e_gs, "unit": "Gsamples/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(n * res * res * 4),
-                "ms_per_step": e2e_ms_max / args.steps, "projections_512_per_s": rays / e2e_secs / 262144.0,
-                "api": "XRayRenderVolumeExCUDA" if is_volume else "XRayRenderSceneCUDA", "note": "host buffers; images land in pinned host memory"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roof,
-        "wall_s_timed_region": t_wall,
+        "metric": "Gsamples/s", "value": main["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32" if is_volume else "f64 intervals / f32 images", "data": "synthetic",
+        "projections_512_per_s": main["projections_512_per_s"], "rays_per_s": main["rays_per_s"],
+        "config": {"workload": main["workload"], "views_total": main["views_rendered"],
+                   "sharding": "views modulo rank (main.go:244 --jobs_modulo/--job); fixed view list, so N ranks share the same work",
+                   "mode": "fp32-mode request (|dI| <= 1e-4); scenes of convex primitives take the interval renderer, whose intervals are fp64",
+                   "l2": "256 MiB buffer rewritten between timed steps; the step's output (>= 1.5 GB on one GPU) exceeds the 126 MB L2"},
+        "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "roofline": main["roofline"],
+        "parity_spot_check": main["parity_spot_check"], "work_per_step": main["work_per_step"], "wall_s_timed_region": main["wall_s_timed_region"],
     }
-    if is_volume and world == 1 and not args.no_ref_cuda:
-        line["reference_cuda"] = time_reference_cuda_plugin(X, vol_np, cams, res, ds_v, ref_samples / args.steps, local_rank)
+    if "reference_cuda" in main:
+        line["reference_cuda"] = main["reference_cuda"]
+    if subs:
+        for r in subs.values():
+            r.pop("clocks", None)
+        line["configs"] = subs
     if world == 1 and not args.no_cpu:
-        cb = cpu_baseline(args.workload, budget_s=args.cpu_budget)
+        cb = cpu_baseline(args.workload, budget_s=args.cpu_budget, volume=volume if is_volume else None)
         line["cpu_baseline"] = {"value": cb["gsamples_per_s"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": cb["kind"],
                                 "sample": cb["sample"], "projections_512_per_s": cb["rays_per_s"] / 262144.0}
+        for key, name, _ in SUB_CONFIGS:
+            if key in subs:
+                c2 = cpu_baseline(name, budget_s=max(3.0, args.cpu_budget / 4), volume=volume if name == "voxel1024" else None)
+                subs[key]["cpu_baseline"] = {"value": c2["gsamples_per_s"], "unit": "Gsamples/s", "cores": c2["cores"], "kind": c2["kind"],
+                                             "sample": c2["sample"]}
     print(json.dumps(line), flush=True)
 
 
@@ -497,12 +606,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lattice", choices=sorted(WORKLOADS))
-    ap.add_argument("--views", type=int, default=0, help="override views per GPU (diagnostics only)")
-    ap.add_argument("--res", type=int, default=0, help="override detector size (diagnostics only)")
-    ap.add_argument("--integ", default="", choices=["", "simple", "hierarchical"], help="override the integrator (diagnostics only)")
+    ap.add_argument("--views", type=int, default=0, help="override the total number of views (diagnostics only)")
     ap.add_argument("--volume-n", type=int, default=1024)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only (skip the cfg1/3/4/5 sub-records)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference CUDA plugin (voxel workload)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -104,7 +104,7 @@ typedef struct {
                                   [3] primitive tests executed       [4] rays
                                   [5] kernel launches
                                   [6] image tiles the interval renderer handed to the marching kernels
-                                  [7] why (OR of reason bits, render_span.cu) */
+                                  [7] why (OR of reason bits, render_span.cu); bit 16 = the interval renderer ran */
     int32_t view_begin;        /* first camera's global view index (for sharding bookkeeping only) */
     int32_t reserved[7];
 } XRayRenderOpts;
@@ -146,8 +146,12 @@ int XRayCameraFromAngles(double azimuthal_deg, double polar_deg, double R, doubl
  * out_images[cam*res*res + i*res + j] of opts->out_dtype.  Synchronous. */
 int XRayRenderSceneCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
                         const XRayRenderOpts* opts, void* out_images);
-/* Same, into a DEVICE buffer on the current device; enqueued on opts->stream, returns
- * without synchronising.  cameras is a host array (copied before return). */
+/* Same, into a DEVICE buffer on the current device.  The kernels are enqueued on opts->stream and the call returns
+ * without waiting for THEM; the caller orders later work after them on that stream (or synchronises it).  The call may
+ * block the host on earlier work: the library keeps one set of per-device scratch (cameras, sample-lattice tables),
+ * so it first waits for the previous call on this device -- whatever stream that one used -- to finish reading it, and a
+ * scene's first use on a device uploads it synchronously.  cameras is a host array (copied before return).  With
+ * opts->stats set the call synchronises the stream to read the counters back. */
 int XRayRenderSceneDeviceCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
                               const XRayRenderOpts* opts, void* d_out_images);
 
@@ -157,7 +161,9 @@ int XRayRenderSceneDeviceCUDA(XRayScene* scene, const XRayCameraParams64* camera
 int XRayRenderVolumeExCUDA(const void* volume, int volume_dtype, int nx, int ny, int nz,
                            const XRayCameraParams64* cameras, int num_cameras, int image_res,
                            const XRayRenderOpts* opts, void* out_images);
-/* Device-resident volume (fp32, reference layout) and device images; async on opts->stream. */
+/* Device-resident volume (fp32, reference layout) and device images, enqueued on opts->stream.  The volume is wrapped in
+ * a temporary scene that is released before the call returns, which waits for the enqueued kernels: this entry point is
+ * synchronous with respect to its own work (the images are complete on return). */
 int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
                                int num_cameras, int image_res, const XRayRenderOpts* opts, void* d_out_images);
 

@@ -1,6 +1,10 @@
-timeout 1500 python -m pytest tests/test_gpu_span.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_properties.py -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu_r2d.txt; tail -8 gpurun_out/pytest_gpu_r2d.txt
-python tools/span_reasons.py 2>&1 | grep -v simple | tee gpurun_out/span_reasons3.txt
-python tools/span_time.py lattice pillar cube box_w_pped balls lattice_linear 2>&1 | tee gpurun_out/span_time8.txt
-XRAY_SPAN_NO_BINS=1 python tools/span_time.py lattice pillar cube box_w_pped balls 2>&1 | tee -a gpurun_out/span_time8.txt
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_span8.csv python tools/render_once.py lattice.json 1024 16 - 2 > /dev/null 2>&1
-grep -v "^==" gpurun_out/launches_span8.csv | cut -d, -f5,12- | tail -8
+python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; tail -3 gpurun_out/bench_r2a.err; python -c "
+import json
+d=json.load(open('gpurun_out/bench_r2a.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['ms_per_step'],'pinned',d['e2e']['pinned'])
+print('roof',d['roofline']['frac'],d['parity_spot_check'])
+print('cpu',d.get('cpu_baseline'))
+for k,v in d.get('configs',{}).items():
+    print(k,'value',round(v['value'],1),'ms',round(v['ms_per_step'],3),'e2e',round(v['e2e']['value'],1),round(v['e2e']['ms_per_step'],2),'pin',round(v['e2e']['pinned']['value'],1),'spot',v['parity_spot_check']['max_abs_dI'],'roof',v['roofline']['frac'], v.get('cpu_baseline',{}).get('value'), v.get('reference_cuda',{}).get('speedup'))
+"
+python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_r2a_ref.json 2>&1; cat gpurun_out/bench_r2a_ref.json | cut -c1-600

@@ -125,6 +125,27 @@ static void stage_release_locked() {
     g_stage_dev = -1;
 }
 
+// Host-side copy out of pinned staging into the caller's pageable buffer, split over a few threads: one core moves
+// ~8-10 GB/s, the PCIe link delivers ~55, and a cgo / ctypes caller always hands over pageable memory.
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    int T = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / ((size_t)4 << 20)));
+    const unsigned hc = std::thread::hardware_concurrency();
+    if (hc > 0) T = std::min<int>(T, std::max(1u, hc / 2));
+    if (const char* e = getenv("XRAY_DRAIN_THREADS")) T = std::max(1, std::min(32, atoi(e)));
+    if (T <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < T; ++t) {
+        const size_t off = std::min(bytes, per * t), end = std::min(bytes, per * (t + 1));
+        if (end > off) th.emplace_back([=] { memcpy((unsigned char*)dst + off, (const unsigned char*)src + off, end - off); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto& t : th) t.join();
+}
+
 static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int dev, cudaStream_t stream) {
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess &&
@@ -396,8 +417,15 @@ struct DevCtx {
     unsigned char* vol_occ[2] = {nullptr, nullptr};
     size_t vol_occ_cap = 0;
     // tiles the span renderer hands to the marching kernels: compacted ids (one slot per CTA of a launch) + their count
-    unsigned int* d_tile_list = nullptr;
+    unsigned int* d_tile_list[2] = {nullptr, nullptr};  // one per output buffer of the double-buffered host path
     size_t tile_list_cap = 0;
+    // The scratch above (cameras, lattice tables, stats, bins ...) is shared by every call on this device, and the device-output
+    // entry points return with their kernels still in flight on the caller's stream.  ev_busy marks the end of the last call's
+    // work; the next call -- whatever stream it uses -- waits for it before it touches the scratch.
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
+    cudaStream_t aux_stream = nullptr;        // hand-over pass of batch b runs here, beside the span kernel of batch b + 1
+    cudaEvent_t ev_span[2] = {nullptr, nullptr};
     // screen-space bins of the span renderer: per (view, tile) a count and bin_cap instance codes
     unsigned int* d_bins = nullptr;
     size_t bins_cap_words = 0;
@@ -436,9 +464,21 @@ static void ctx_release(DevCtx* c) {
         c->vol_occ[b] = nullptr;
     }
     c->vol_occ_cap = 0;
-    if (c->d_tile_list) cudaFree(c->d_tile_list);
-    c->d_tile_list = nullptr;
+    for (int b = 0; b < 2; ++b) {
+        if (c->d_tile_list[b]) cudaFree(c->d_tile_list[b]);
+        c->d_tile_list[b] = nullptr;
+        if (c->ev_span[b]) cudaEventDestroy(c->ev_span[b]);
+        c->ev_span[b] = nullptr;
+    }
     c->tile_list_cap = 0;
+    if (c->ev_busy) cudaEventDestroy(c->ev_busy);
+    c->ev_busy = nullptr;
+    c->busy = false;
+    if (c->aux_stream) {
+        cudaStreamSynchronize(c->aux_stream);
+        cudaStreamDestroy(c->aux_stream);
+    }
+    c->aux_stream = nullptr;
     if (c->d_bins) cudaFree(c->d_bins);
     c->d_bins = nullptr;
     c->bins_cap_words = 0;
@@ -480,6 +520,10 @@ static int run_job(Job& J) {
     } while (0)
     if (!C->stream) CUJ(3, cudaStreamCreateWithFlags(&C->stream, cudaStreamNonBlocking));
     cudaStream_t stream = J.use_user_stream ? J.user_stream : C->stream;
+    if (C->busy) {  // an earlier call (possibly on another stream) may still be reading the per-device scratch
+        CUJ(7, cudaEventSynchronize(C->ev_busy));
+        C->busy = false;
+    }
     const int nv = (int)J.views.size();
     if (nv == 0) return 0;
     const int res = J.res;
@@ -708,10 +752,14 @@ static int run_job(Job& J) {
         const size_t need = (size_t)max_batch * P.tiles_i * P.tiles_j * 4;  // warp tiles
         if (need > C->tile_list_cap) {
             CUJ(7, cudaStreamSynchronize(stream));
-            if (C->d_tile_list) cudaFree(C->d_tile_list);
-            C->d_tile_list = nullptr;
+            if (C->aux_stream) CUJ(7, cudaStreamSynchronize(C->aux_stream));
+            for (int b = 0; b < 2; ++b) {
+                if (C->d_tile_list[b]) cudaFree(C->d_tile_list[b]);
+                C->d_tile_list[b] = nullptr;
+            }
             C->tile_list_cap = 0;
-            CUJ(3, cudaMalloc(&C->d_tile_list, (need + 2) * sizeof(unsigned int)));  // [0] = count, [1] = work counter, [2..] = ids
+            for (int b = 0; b < 2; ++b)
+                CUJ(3, cudaMalloc(&C->d_tile_list[b], (need + 2) * sizeof(unsigned int)));  // [0] = count, [1] = work counter, [2..] = ids
             C->tile_list_cap = need;
         }
     }
@@ -759,7 +807,7 @@ static int run_job(Job& J) {
             }
         }
     }
-    auto launch_march = [&]() -> cudaError_t {
+    auto launch_march = [&](cudaStream_t stream) -> cudaError_t {  // (shadows the job's stream on purpose)
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
                                             h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, (int)(P.cams - C->d_cams), P.n_views), vol_occ, stream);
@@ -773,26 +821,35 @@ static int run_job(Job& J) {
                                       stream);
         return launch_render_scene(P, J.opts.precision, J.opts.integration, stream);
     };
-    auto launch = [&](int v0, int n, void* d_dst) -> cudaError_t {
+    // parity: which tile list / event to use; march_stream: where the hand-over pass goes (the job's stream, or the auxiliary
+    // one, so that it overlaps the next batch's span kernel -- a handful of hard warp tiles take ~1 ms on their own)
+    auto launch = [&](int v0, int n, void* d_dst, int parity, cudaStream_t march_stream) -> cudaError_t {
         ++n_launches;
         P.cams = C->d_cams + v0;
         P.n_views = n;
         P.out = d_dst;
+        P.out_vec4 = ((uintptr_t)d_dst % 16 == 0 && img_bytes % 16 == 0) ? 1 : 0;  // 128-bit stores need a 16-byte aligned image base
         P.tile_list = nullptr;
         P.tile_count = nullptr;
         // the grid is one CTA per (view, tile); keep it below 2^31
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
-        if (!use_span) return launch_march();
+        if (!use_span) return launch_march(stream);
+        unsigned int* tl = C->d_tile_list[parity];
         cudaError_t es = launch_render_span(P, J.opts.integration, P.stats != nullptr, C->d_nfine, ds->d_blob + h->span_off, h->span_bytes,
-                                            C->d_tile_list + 2, C->d_tile_list, bin_cap ? C->d_bins : nullptr, bin_cap, n_instances, stream);
+                                            tl + 2, tl, bin_cap ? C->d_bins : nullptr, bin_cap, n_instances, stream);
         if (es != cudaSuccess) return es;
 #ifdef XRAY_DEV_KNOBS
         if (P.dbg_cause == 77) return es;  // leave the interval renderer's hand-over codes in the image
 #endif
         ++n_launches;
-        P.tile_list = C->d_tile_list + 2;
-        P.tile_count = C->d_tile_list;
-        es = launch_march();
+        if (march_stream != stream) {
+            es = cudaEventRecord(C->ev_span[parity], stream);
+            if (es == cudaSuccess) es = cudaStreamWaitEvent(march_stream, C->ev_span[parity], 0);
+            if (es != cudaSuccess) return es;
+        }
+        P.tile_list = tl + 2;
+        P.tile_count = tl;
+        es = launch_march(march_stream);
         P.tile_list = nullptr;
         P.tile_count = nullptr;
         return es;
@@ -804,7 +861,7 @@ static int run_job(Job& J) {
         while (v < nv) {
             int n = 1;
             while (v + n < nv && n < max_batch && J.views[v + n] == J.views[v + n - 1] + 1) ++n;
-            CUJ(5, launch(v, n, (unsigned char*)J.out + (size_t)J.views[v] * img_bytes));
+            CUJ(5, launch(v, n, (unsigned char*)J.out + (size_t)J.views[v] * img_bytes, 0, stream));
             v += n;
         }
     } else {
@@ -838,15 +895,28 @@ static int run_job(Job& J) {
         }
         if (!C->copy_stream) CUJ(3, cudaStreamCreateWithFlags(&C->copy_stream, cudaStreamNonBlocking));
         cudaStream_t cstream = C->copy_stream;
+        cudaStream_t mstream = stream;
+        if (use_span) {
+            if (!C->aux_stream) CUJ(3, cudaStreamCreateWithFlags(&C->aux_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b)
+                if (!C->ev_span[b]) CUJ(3, cudaEventCreateWithFlags(&C->ev_span[b], cudaEventDisableTiming));
+            mstream = C->aux_stream;
+        }
         int pend_v0[2] = {0, 0}, pend_n[2] = {0, 0};
         auto drain = [&](int b) -> cudaError_t {  // copy batch b from pinned staging into the caller's buffer
             if (pend_n[b] == 0) return cudaSuccess;
             cudaError_t ee = cudaEventSynchronize(C->ev[b]);
             if (ee != cudaSuccess) return ee;
-            if (!out_pinned)
-                for (int k = 0; k < pend_n[b]; ++k)
-                    memcpy((unsigned char*)J.out + (size_t)J.views[pend_v0[b] + k] * img_bytes, C->h_pin[b] + (size_t)k * img_bytes,
-                           img_bytes);
+            if (!out_pinned) {
+                int k = 0;  // contiguous runs of views move in one (multi-threaded) copy each
+                while (k < pend_n[b]) {
+                    int m = 1;
+                    while (k + m < pend_n[b] && J.views[pend_v0[b] + k + m] == J.views[pend_v0[b] + k + m - 1] + 1) ++m;
+                    parallel_memcpy((unsigned char*)J.out + (size_t)J.views[pend_v0[b] + k] * img_bytes, C->h_pin[b] + (size_t)k * img_bytes,
+                                    (size_t)m * img_bytes);
+                    k += m;
+                }
+            }
             pend_n[b] = 0;
             return cudaSuccess;
         };
@@ -854,8 +924,8 @@ static int run_job(Job& J) {
         while (v < nv) {
             int n = std::min(max_batch, nv - v);
             CUJ(7, drain(b));  // buffer b is free again once its previous batch reached the caller
-            CUJ(5, launch(v, n, C->d_img[b]));
-            CUJ(7, cudaEventRecord(C->evk[b], stream));
+            CUJ(5, launch(v, n, C->d_img[b], b, mstream));
+            CUJ(7, cudaEventRecord(C->evk[b], mstream));  // the batch is complete once its hand-over pass is
             CUJ(7, cudaStreamWaitEvent(cstream, C->evk[b], 0));
             if (out_pinned) {
                 // contiguous runs of views go out in one copy each
@@ -878,6 +948,7 @@ static int run_job(Job& J) {
         }
         CUJ(7, drain(b));
         CUJ(7, drain(b ^ 1));
+        if (mstream != stream) CUJ(7, cudaStreamSynchronize(mstream));  // (already idle: both drains waited on its batches)
     }
     if (J.opts.stats) {
         CUJ(8, cudaMemcpyAsync(J.stats, C->d_stats, sizeof(unsigned long long) * XRAY_NUM_STATS, cudaMemcpyDeviceToHost, stream));
@@ -885,6 +956,10 @@ static int run_job(Job& J) {
         J.stats[5] = n_launches;
     } else if (!J.out_on_device) {
         CUJ(7, cudaStreamSynchronize(stream));
+    } else {
+        if (!C->ev_busy) CUJ(3, cudaEventCreateWithFlags(&C->ev_busy, cudaEventDisableTiming));
+        CUJ(7, cudaEventRecord(C->ev_busy, stream));
+        C->busy = true;
     }
     return 0;
 #undef CUJ
@@ -1105,11 +1180,26 @@ void XRayRenderOptsInit(XRayRenderOpts* o) {
     o->density_multiplier = 1.0;
 }
 
-int XRaySceneCompileJSON(const char* object_json, const char* deformation_json, XRayScene** out_scene) {
+// No C++ exception may cross the C boundary (a cgo / ctypes caller would be terminated): allocation failures become error 9.
+#define XR_NOTHROW(expr)                                                        \
+    try {                                                                       \
+        return (expr);                                                          \
+    } catch (const std::bad_alloc&) {                                           \
+        return fail(9, "out of host memory");                                   \
+    } catch (const std::exception& ex) {                                        \
+        return fail(9, std::string("internal error: ") + ex.what());            \
+    } catch (...) {                                                             \
+        return fail(9, "internal error");                                       \
+    }
+
+static int compile_json_impl(const char* object_json, const char* deformation_json, XRayScene** out_scene) {
     std::string err;
     int rc = compile_scene_json(object_json, deformation_json, out_scene, err);
     if (rc) return fail(rc, err);
     return 0;
+}
+int XRaySceneCompileJSON(const char* object_json, const char* deformation_json, XRayScene** out_scene) {
+    XR_NOTHROW(compile_json_impl(object_json, deformation_json, out_scene))
 }
 
 void XRaySceneFree(XRayScene* scene) {
@@ -1177,12 +1267,12 @@ int XRayCameraFromAngles(double azimuthal_deg, double polar_deg, double R, doubl
 
 int XRayRenderSceneCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
                         const XRayRenderOpts* opts, void* out_images) {
-    return render_common(scene, cameras, num_cameras, image_res, opts, out_images, false, nullptr, false);
+    XR_NOTHROW(render_common(scene, cameras, num_cameras, image_res, opts, out_images, false, nullptr, false))
 }
 
 int XRayRenderSceneDeviceCUDA(XRayScene* scene, const XRayCameraParams64* cameras, int num_cameras, int image_res,
                               const XRayRenderOpts* opts, void* d_out_images) {
-    return render_common(scene, cameras, num_cameras, image_res, opts, d_out_images, true, nullptr, false);
+    XR_NOTHROW(render_common(scene, cameras, num_cameras, image_res, opts, d_out_images, true, nullptr, false))
 }
 
 }  // extern "C"
@@ -1205,7 +1295,7 @@ static bool volume_fast_path_ok(const XRayRenderOpts& o, int dtype) {
 extern "C" {
 
 int XRayRenderVolumeExCUDA(const void* volume, int volume_dtype, int nx, int ny, int nz, const XRayCameraParams64* cameras,
-                           int num_cameras, int image_res, const XRayRenderOpts* opts, void* out_images) {
+                           int num_cameras, int image_res, const XRayRenderOpts* opts, void* out_images) try {
     if (!volume || !cameras || !out_images) return fail(1, "null pointer argument");
     if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
     XRayScene* sc = nullptr;
@@ -1220,10 +1310,14 @@ int XRayRenderVolumeExCUDA(const void* volume, int volume_dtype, int nx, int ny,
     XRaySceneFree(sc);
     g_last_error = keep;
     return rc;
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
 int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
-                               int num_cameras, int image_res, const XRayRenderOpts* opts, void* d_out_images) {
+                               int num_cameras, int image_res, const XRayRenderOpts* opts, void* d_out_images) try {
     if (!d_volume || !cameras || !d_out_images) return fail(1, "null pointer argument");
     if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
     XRayScene* sc = nullptr;
@@ -1237,9 +1331,13 @@ int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, co
     XRaySceneFree(sc);
     g_last_error = keep;
     return rc;
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
-int XRayVoxelizeSceneCUDA(XRayScene* scene, int res, double density_multiplier, float* out_volume) {
+int XRayVoxelizeSceneCUDA(XRayScene* scene, int res, double density_multiplier, float* out_volume) try {
     if (!scene || !out_volume) return fail(1, "null pointer argument");
     if (res <= 0) return fail(2, "res must be positive");
     int dev = 0;
@@ -1261,6 +1359,10 @@ int XRayVoxelizeSceneCUDA(XRayScene* scene, int res, double density_multiplier, 
     cudaFree(d_out);
     if (e != cudaSuccess) return fail_cuda(5, "voxelize", e);
     return 0;
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
 int XRayMeasureFp32Peak(double* tflops) {
@@ -1300,7 +1402,7 @@ static void legacy_devices(XRayRenderOpts& o) {
 }
 
 int RenderVolumeProjectionsCUDA(const float* volume, int nx, int ny, int nz, const XRayCameraParams* cameras, int num_cameras,
-                                int image_res, float ds, float flat_field, float* out_images) {
+                                int image_res, float ds, float flat_field, float* out_images) try {
     if (!volume || !cameras || !out_images) return fail(1, "null pointer argument");  // cuda_backend.cu:95-97
     if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
     if (!(ds > 0.0f)) return fail(2, "ds must be positive");
@@ -1323,6 +1425,10 @@ int RenderVolumeProjectionsCUDA(const float* volume, int nx, int ny, int nz, con
     o.density_multiplier = 1.0;
     legacy_devices(o);
     return XRayRenderVolumeExCUDA(volume, XRAY_VOXEL_F32, nx, ny, nz, cams.data(), num_cameras, image_res, &o, out_images);
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
 static int assemble_common(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier, int grid_dim,
@@ -1330,7 +1436,7 @@ static int assemble_common(const CylinderParams* cylinders, int num_cylinders, i
     if (!cylinders || !out_volume) return fail(1, "null pointer argument");
     if (num_cylinders <= 0 || res <= 0) return fail(2, "num_cylinders and res must be positive");
     const size_t total = (size_t)res * res * res;
-    CU(3, cudaSetDevice(0));
+    // runs on the calling thread's current device, like the reference plugin (which never selects one)
     CylinderParams* d_cyl = nullptr;
     int *d_off = nullptr, *d_idx = nullptr;
     float* d_out = nullptr;
@@ -1366,13 +1472,17 @@ static int assemble_common(const CylinderParams* cylinders, int num_cylinders, i
 }
 
 int AssembleVoxelGridCUDA(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier,
-                          float* out_volume) {
+                          float* out_volume) try {
     return assemble_common(cylinders, num_cylinders, res, density_multiplier, 0, nullptr, nullptr, 0, out_volume);
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
 int AssembleVoxelGridSpatialCUDA(const CylinderParams* cylinders, int num_cylinders, int res, float density_multiplier,
                                  int grid_dim, const int* cell_offsets, const int* cyl_indices, int num_cyl_indices,
-                                 float* out_volume) {
+                                 float* out_volume) try {
     if (!cell_offsets || (!cyl_indices && num_cyl_indices > 0)) return fail(1, "null pointer argument");
     if (grid_dim <= 0 || num_cyl_indices < 0) return fail(2, "grid_dim must be positive");
     // validate the caller's CSR before trusting it on the device
@@ -1384,6 +1494,10 @@ int AssembleVoxelGridSpatialCUDA(const CylinderParams* cylinders, int num_cylind
         if (cyl_indices[k] < 0 || cyl_indices[k] >= num_cylinders) return fail(2, "cyl_indices entry out of range");
     return assemble_common(cylinders, num_cylinders, res, density_multiplier, grid_dim, cell_offsets, cyl_indices,
                            num_cyl_indices, out_volume);
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
 }
 
 }  // extern "C"

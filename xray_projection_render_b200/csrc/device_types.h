@@ -49,6 +49,7 @@ struct RenderParams {
     double aabb_lo[3], aabb_hi[3];
     void* out;
     int out_f64;
+    int out_vec4;               // the output pointer of this launch allows 128-bit stores (16-byte aligned image rows)
     int prog_in_smem;           // stage instr + fp32 pool in shared memory
     unsigned int smem_prog_bytes;
     unsigned long long* stats;  // device, XRAY_NUM_STATS counters or null

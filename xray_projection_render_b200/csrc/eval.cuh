@@ -787,7 +787,7 @@ __device__ __forceinline__ void store_pixel(const RenderParams& P, int view, int
     float v2 = __shfl_down_sync(FULL_MASK, v, 2);
     float v3 = __shfl_down_sync(FULL_MASK, v, 3);
     float* out = reinterpret_cast<float*>(P.out);
-    if (kWarpJ % 4 == 0 && (P.res & 3) == 0) {
+    if (kWarpJ % 4 == 0 && (P.res & 3) == 0 && P.out_vec4) {
         if ((threadIdx.x & 3) == 0 && valid) *reinterpret_cast<float4*>(out + idx) = make_float4(v, v1, v2, v3);
     } else if (valid) {
         out[idx] = v;

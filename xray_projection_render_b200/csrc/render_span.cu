@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         const int n16 = (int)((SA.section_bytes + 15u) >> 4);
         for (int k = tid; k < n16; k += kBlockThreads) dst[k] = __ldg(src + k);
     }
+    if (COUNT && P.stats && blockIdx.x == 0 && tid == 0) atomicOr(P.stats + 7, 0x10000ull);  // "the interval renderer ran"
     const SpanHeader& H = *reinterpret_cast<const SpanHeader*>(smem);
     unsigned int* cand = reinterpret_cast<unsigned int*>(smem + ((SA.section_bytes + 15u) & ~15u));
     // interval q is written after candidate q has been read and there are never more intervals than candidates read, so
@@ -406,6 +407,10 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             for (unsigned int q = 0; q < nb; ++q) {
                 const unsigned int code = __ldg(bl + q);
                 const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
+                if (deg_axis >= 0) {  // a ray inside a face plane only ever folds into the two periods either side of it
+                    const int pa = deg_axis == 0 ? px : (deg_axis == 1 ? py : pz);
+                    if (pa != dg.nA && pa != dg.nB) continue;
+                }
                 if (hit)
                     test_and_push((int)(code & 63u), (int)(code & ~63u), fcx - (float)px * ucdx + ulx, fcy - (float)py * ucdy + uly,
                                   fcz - (float)pz * ucdz + ulz);
