@@ -6,6 +6,8 @@
  *
  *   host_loader_replay <lib> symbols   -> load + resolve, argument validation (no GPU needed)
  *   host_loader_replay <lib> probe     -> the 1x1x1 probe render and a small voxelisation (needs a GPU)
+ *   host_loader_replay <lib> scene     -> the call sequence integration/go_host.patch adds to the host (cuda_dl_RenderSceneCUDA):
+ *                                         six optional symbols, compile object + deformation JSON, render, free (needs a GPU)
  * Exit code 0 = everything behaved as the Go host expects.  Test infrastructure, not product code. */
 #include <dlfcn.h>
 #include <math.h>
@@ -110,6 +112,61 @@ static int check_probe(struct plugin* p) {
     return 0;
 }
 
+/* integration/go_host.patch, cuda_backend.go cuda_dl_load + cuda_dl_RenderSceneCUDA: the JSON is what json.Marshal of
+ * lat[0].ToMap() / df[0].ToMap() produces (objects.go / deformations.go ToMap methods). */
+static int check_scene(struct plugin* p) {
+    typedef int (*compile_fn)(const char*, const char*, XRayScene**);
+    typedef void (*free_fn)(XRayScene*);
+    typedef int (*slots_fn)(const XRayScene*);
+    typedef void (*optsinit_fn)(XRayRenderOpts*);
+    typedef int (*render_scene_fn)(XRayScene*, const XRayCameraParams64*, int, int, const XRayRenderOpts*, void*);
+    typedef const char* (*lasterr_fn)(void);
+    compile_fn compile = (compile_fn)dlsym(p->handle, "XRaySceneCompileJSON");
+    free_fn sfree = (free_fn)dlsym(p->handle, "XRaySceneFree");
+    slots_fn slots = (slots_fn)dlsym(p->handle, "XRaySceneNumVoxelSlots");
+    optsinit_fn optsinit = (optsinit_fn)dlsym(p->handle, "XRayRenderOptsInit");
+    render_scene_fn render_scene = (render_scene_fn)dlsym(p->handle, "XRayRenderSceneCUDA");
+    lasterr_fn lasterr = (lasterr_fn)dlsym(p->handle, "XRayLastError");
+    EXPECT(compile && sfree && slots && optsinit && render_scene && lasterr);
+    const char* obj = "{\"type\":\"object_collection\",\"greedy_dens_eval\":false,\"objects\":["
+                      "{\"type\":\"sphere\",\"center\":[0,0,0],\"radius\":0.5,\"rho\":1}]}";
+    const char* def = "{\"type\":\"rigid\",\"displacements\":[0,0,0]}";
+    XRayScene* sc = NULL;
+    EXPECT(compile(obj, def, &sc) == 0 && sc != NULL);
+    EXPECT(slots(sc) == 0);
+    /* camera on the +x axis looking at the origin: columns of view = camera axes (s, u, -f), translation = eye */
+    XRayCameraParams64 cam;
+    memset(&cam, 0, sizeof(cam));
+    cam.eye[0] = 4.0;
+    cam.view[0 * 4 + 2] = 1.0; cam.view[0 * 4 + 3] = 4.0; /* world x = cam z + 4  (camera looks down -z = -x) */
+    cam.view[1 * 4 + 0] = 1.0;                            /* world y = cam x */
+    cam.view[2 * 4 + 1] = 1.0;                            /* world z = cam y */
+    cam.view[15] = 1.0;
+    cam.fov_y = 40.0;
+    cam.R = 4.0;
+    XRayRenderOpts o;
+    optsinit(&o);
+    EXPECT(o.struct_size == sizeof(XRayRenderOpts));
+    o.integration = XRAY_INTEGRATE_SIMPLE;
+    o.ds = 1.0e-3;
+    o.flat_field = 0.0;
+    o.density_multiplier = 1.0;
+    enum { RES = 4 };
+    float out[RES * RES];
+    int rc = render_scene(sc, &cam, 1, RES, &o, out);
+    if (rc != 0) fprintf(stderr, "XRayRenderSceneCUDA: %d %s\n", rc, lasterr());
+    EXPECT(rc == 0);
+    /* pixel (RES/2, RES/2) is the central ray: a chord of length 1 through the unit-density sphere (main_test.go:326-361) */
+    EXPECT(fabsf(out[(RES / 2) * RES + RES / 2] - expf(-1.0f)) < 2.0e-3f);
+    EXPECT(out[0] == 1.0f); /* the corner ray misses */
+    sfree(sc);
+    /* errors come back as codes plus text, never as a crash */
+    sc = NULL;
+    EXPECT(compile("{\"type\":\"nonsense\"}", NULL, &sc) != 0);
+    EXPECT(lasterr()[0] != 0);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) {
         fprintf(stderr, "usage: %s <libcuda_render.so | -> <symbols|probe>\n", argv[0]);
@@ -124,7 +181,7 @@ int main(int argc, char** argv) {
     struct plugin p;
     int rc = plugin_load(&p, path);
     if (rc != 0) return -rc; /* 1 / 2 */
-    rc = strcmp(argv[2], "probe") == 0 ? check_probe(&p) : check_symbols(&p);
+    rc = strcmp(argv[2], "probe") == 0 ? check_probe(&p) : (strcmp(argv[2], "scene") == 0 ? check_scene(&p) : check_symbols(&p));
     if (rc == 0) printf("ok %s\n", argv[2]);
     return rc ? 10 : 0;
 }

@@ -189,10 +189,11 @@ def test_renderer_end_to_end_files(X, O, scenes, tmp_path):
     import zlib, struct
     data = (out_dir / "image_001.png").read_bytes()
     raw = zlib.decompress(data[data.index(b"IDAT") + 4:data.index(b"IEND") - 8])
-    px = np.frombuffer(raw, dtype=np.uint8).reshape(64, 1 + 64 * 4)[:, 1:].reshape(64, 64, 4)
+    assert data[25] == 2  # opaque frame: 8-bit RGB, as Go's png.Encode writes an opaque *image.RGBA
+    px = np.frombuffer(raw, dtype=np.uint8).reshape(64, 1 + 64 * 3)[:, 1:].reshape(64, 64, 3)
     osc = O.OracleScene(str(scenes / "cube_w_hole.json"), flat_field=0.1)
     ref, _ = osc.render_view(eye, cm, 64, 40.0, 4.0, osc.auto_ds(), "hierarchical")
-    want = X.image_to_rgba8(ref)
+    want = X.image_to_rgba8(ref)[..., :3]
     assert np.abs(px.astype(int) - want.astype(int)).max() <= 1
     assert (px == want).mean() > 0.999
     bad = r.render({"input": str(tmp_path / "missing.json"), "output_dir": str(out_dir)})

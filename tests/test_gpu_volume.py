@@ -286,3 +286,6 @@ def test_go_host_probe_from_c(X, host_replay):
     lib = str(Path(X.__file__).resolve().parent / "lib" / "libcuda_render.so")
     r = subprocess.run([host_replay, lib, "probe"], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok probe", r.stderr
+    # the analytic-scene call sequence integration/go_host.patch adds to the host (compile JSON, render, free)
+    r = subprocess.run([host_replay, lib, "scene"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok scene", r.stderr

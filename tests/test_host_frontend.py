@@ -250,15 +250,38 @@ def test_png_quantisation_and_orientation(X, tmp_path):
     assert (rgba[..., 3] == 255).all()
     t = X.image_to_rgba8(img, transparency=True)
     assert t[0, 1, 3] == 0 and t[1, 0, 3] == 255  # alpha 0 only where val == 1 (main.go:486-492)
+    assert tuple(t[0, 1]) == (0, 0, 0, 0)          # png.Encode un-premultiplies: alpha 0 -> colour 0
+    # Go's png.Encode of an opaque *image.RGBA writes 8-bit RGB (colour type 2) ...
     p = tmp_path / "x.png"
     X.write_png(str(p), rgba)
     data = p.read_bytes()
     assert data[:8] == b"\x89PNG\r\n\x1a\n"
     w, h, depth, ctype = struct.unpack(">IIBB", data[16:26])
-    assert (w, h, depth, ctype) == (2, 2, 8, 6)
+    assert (w, h, depth, ctype) == (2, 2, 8, 2)
     idat = data[data.index(b"IDAT") + 4:data.index(b"IEND") - 8]
     raw = zlib.decompress(idat)
-    assert raw == b"".join(b"\x00" + rgba[y].tobytes() for y in range(2))
+    assert raw == b"".join(b"\x00" + rgba[y, :, :3].tobytes() for y in range(2))
+    # ... and 8-bit RGBA (colour type 6) as soon as one pixel is transparent
+    X.write_png(str(p), t)
+    data = p.read_bytes()
+    assert struct.unpack(">IIBB", data[16:26]) == (2, 2, 8, 6)
+    raw = zlib.decompress(data[data.index(b"IDAT") + 4:data.index(b"IEND") - 8])
+    assert raw == b"".join(b"\x00" + t[y].tobytes() for y in range(2))
+
+
+def test_object_json_follows_the_reference_tomap_schema(X, scenes):
+    """main.go:538-546 writes lat[0].ToMap(): per type exactly the keys of the ToMap methods (objects.go) -- no greedy flag,
+    voxel grids as nx / ny / nz / dtype float64 / path."""
+    from xray_projection_render_b200.scene import reference_object_map
+
+    sc = X.Scene(str(scenes / "lattice.json"))
+    m = reference_object_map(sc.object_map)
+    assert set(m) == {"type", "uc", "xmin", "xmax", "ymin", "ymax", "zmin", "zmax"}
+    assert set(m["uc"]) == {"type", "objects", "xmin", "xmax", "ymin", "ymax", "zmin", "zmax"} and m["uc"]["type"] == "unit_cell"
+    assert set(m["uc"]["objects"]) == {"type", "objects"}
+    assert set(m["uc"]["objects"]["objects"][0]) == {"type", "p0", "p1", "radius", "rho"}
+    v = reference_object_map({"type": "voxel_grid", "resolution": [4.0, 5.0, 6.0], "path": "vol.raw"})
+    assert v == {"type": "voxel_grid", "nx": 4, "ny": 5, "nz": 6, "dtype": "float64", "path": "vol.raw"}
 
 
 def test_renderer_parameter_validation(X):

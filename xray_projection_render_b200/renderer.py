@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from .camera import (CUBE_HALF_DIAGONAL, camera_matrix, cameras_from_angles, generate_camera_angles, to_legacy)
-from .scene import Scene, SceneError
+from .scene import reference_object_map, Scene, SceneError
 
 
 def _as_cam_array(cams):
@@ -163,22 +163,27 @@ def image_to_rgba8(img: np.ndarray, transparency: bool = False) -> np.ndarray:
     if transparency:
         alpha = np.where(img.astype(np.float64) < 1.0, 255, 0).astype(np.uint8).T[::-1, :]
         rgba[..., 3] = alpha
-        # image.RGBA is alpha-premultiplied: SetRGBA64 with alpha 0 stores the colour as given
+        # image.RGBA is alpha-premultiplied and png.Encode writes it un-premultiplied: a pixel with alpha 0 comes out as
+        # (0, 0, 0, 0) whatever colour SetRGBA64 stored (image/png writer.go, cbTCA8 case)
+        rgba[alpha == 0, 0:3] = 0
     else:
         rgba[..., 3] = 255
     return rgba
 
 
 def write_png(path: str, rgba: np.ndarray) -> None:
+    """Go's png.Encode of an *image.RGBA: 8-bit RGB (colour type 2) when every pixel is opaque, else 8-bit RGBA (type 6)."""
     h, w, _ = rgba.shape
-    raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
+    opaque = bool((rgba[..., 3] == 255).all())
+    rows = np.ascontiguousarray(rgba[..., :3]) if opaque else rgba
+    raw = b"".join(b"\x00" + rows[y].tobytes() for y in range(h))
 
     def chunk(tag: bytes, data: bytes) -> bytes:
         return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
 
     with open(path, "wb") as fh:
         fh.write(b"\x89PNG\r\n\x1a\n")
-        fh.write(chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)))
+        fh.write(chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2 if opaque else 6, 0, 0, 0)))
         fh.write(chunk(b"IDAT", zlib.compress(raw, 6)))
         fh.write(chunk(b"IEND", b""))
 
@@ -286,7 +291,7 @@ class XRayRenderer:
             json.dump(transform_params, fh, indent=2)
         obj_path = os.path.join(os.path.dirname(p["output_dir"]), "object.json")
         with open(obj_path, "w") as fh:
-            json.dump(scene.object_map, fh, indent=2)
+            json.dump(reference_object_map(scene.object_map), fh, indent=2)
         if p["export_volume"]:  # main.go:549-635 (volume.raw, uint8, [z][x][y] with x = i/res*2-1)
             vol = voxelize_scene(scene, res, float(p["density_multiplier"])).astype(np.float64)
             mx = vol.max()

@@ -182,8 +182,34 @@ def normalize_object(d: dict, strict: bool, base_dir: str = ".", _voxels: list |
             raise SceneError("voxel_grid needs a raw file path with a resolution")
         if _voxels is not None:
             _voxels.append(arr)
-        return {"type": t, "resolution": [float(x) for x in dims]}
+        return {"type": t, "resolution": [float(x) for x in dims], "path": path if isinstance(path, str) else ""}
     raise SceneError(f"unknown object type `{t}`" if _top else "unknown object type")
+
+
+def reference_object_map(n: dict) -> dict:
+    """The object as the reference's ``ToMap()`` methods marshal it into object.json (main.go:538-546): per type exactly the
+    keys of objects.go:33-40, 91-98, 139-146, 198-207, 296-304, 370-379 (no greedy flag), 466-477, 523-534, 704-713
+    (nx / ny / nz, dtype always "float64", the raw file's path), 973-981."""
+    t = n["type"]
+    if t == "object_collection":
+        return {"type": t, "objects": [reference_object_map(o) for o in n["objects"]]}
+    if t == "unit_cell":
+        out = {"type": t, "objects": reference_object_map(n["objects"])}
+        out.update({k: n[k] for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")})
+        return out
+    if t == "tessellated_obj_coll":
+        out = {"type": t, "uc": reference_object_map(n["uc"])}
+        out.update({k: n[k] for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")})
+        return out
+    if t == "voxel_grid":
+        nx, ny, nz = (int(v) for v in n["resolution"])
+        return {"type": t, "nx": nx, "ny": ny, "nz": nz, "dtype": "float64", "path": n.get("path", "")}
+    keys = {"sphere": ("center", "radius", "rho"), "cube": ("center", "side", "rho"), "box": ("center", "sides", "rho"),
+            "parallelepiped": ("origin", "v0", "v1", "v2", "rho"), "cylinder": ("p0", "p1", "radius", "rho"),
+            "gyroid": ("center", "scale", "thickness", "rho")}[t]
+    out = {"type": t}
+    out.update({k: n[k] for k in keys})
+    return out
 
 
 def _normalize_collection(d: dict, strict: bool, base_dir: str, voxels) -> dict:
