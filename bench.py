@@ -472,7 +472,10 @@ def measure(X, torch, dist, name, rank, world, local_rank, steps, warmup, flush,
                           "warp_tiles_handed_to_marching_kernels": w["marched_tiles"]},
     }
     if world > 1 and is_volume:
-        rec["e2e"]["broadcast_ms"] = bcast_mean
+        # on the root the interval starts when its own upload is done; the other ranks' intervals include waiting for that upload
+        rec["e2e"]["broadcast_ms"] = float(np.mean(bcast_page)) if bcast_page else None
+        rec["e2e"]["broadcast_ms_max_over_ranks_incl_wait_for_root_upload"] = bcast_mean
+        rec["e2e"]["broadcast_gb_per_s"] = (4.0 * volume_n ** 3 / 1e9) / (rec["e2e"]["broadcast_ms"] / 1e3) if bcast_page else None
     # ---- roofline of the dominant kernel ----
     launches = max(1.0, w["launches"] / world)   # per rank and step
     peak_tflops = X.measure_fp32_peak()

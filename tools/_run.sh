@@ -1,10 +1,7 @@
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err; tail -3 gpurun_out/bench_r2a.err; python -c "
-import json
-d=json.load(open('gpurun_out/bench_r2a.json'))
-print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['ms_per_step'],'pinned',d['e2e']['pinned'])
-print('roof',d['roofline']['frac'],d['parity_spot_check'])
-print('cpu',d.get('cpu_baseline'))
-for k,v in d.get('configs',{}).items():
-    print(k,'value',round(v['value'],1),'ms',round(v['ms_per_step'],3),'e2e',round(v['e2e']['value'],1),round(v['e2e']['ms_per_step'],2),'pin',round(v['e2e']['pinned']['value'],1),'spot',v['parity_spot_check']['max_abs_dI'],'roof',v['roofline']['frac'], v.get('cpu_baseline',{}).get('value'), v.get('reference_cuda',{}).get('speedup'))
-"
-python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_r2a_ref.json 2>&1; cat gpurun_out/bench_r2a_ref.json | cut -c1-600
+tools/ncu_span.sh lattice.json 1024 64 r2c_lattice render_span_kernel
+tools/ncu_span.sh pillar_array.json 4096 8 r2c_pillar render_span_kernel
+tools/ncu_span.sh gyroid_example.json 1024 64 r2c_gyroid render_async_kernel deformation_sigmoid.json
+tools/ncu_span.sh voxel1024 2048 8 r2c_voxel render_volume_tex_kernel
+tools/ncu_span.sh cube_w_hole.json 512 1 r2c_cube render_span_kernel
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-configs > gpurun_out/b_ncu.log 2>&1
+ls gpurun_out | grep r2c | head -40

@@ -176,7 +176,7 @@ struct SpanDegenerate {
 };
 
 template <int INTEG>
-__device__ __noinline__ bool span_degenerate_axis(const RenderParams& P, const unsigned char* __restrict__ nfine, double o_a, double d_a,
+__device__ __forceinline__ bool span_degenerate_axis(const RenderParams& P, const unsigned char* __restrict__ nfine, double o_a, double d_a,
                                                   double lo, double hi, double D, SpanDegenerate& g) {
     auto period = [&](unsigned int e, bool& inside) -> int {
         double s;
