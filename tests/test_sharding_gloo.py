@@ -120,3 +120,37 @@ def test_synthetic_volume_definition():
     want *= float(x * x + y * y + z * z < 0.81)
     assert abs(vol[k, i, j] - want) <= 1e-6
     assert vol[0, 0, 0] == 0.0 and vol.max() <= 1.0
+
+
+def test_reference_arm_line_and_shared_workload_string(capsys):
+    """bench.py --impl reference: one JSON line with the contract's keys, the SAME config.workload string our arm prints
+    (bench.workload_string), at least 3 s of CPU work per step unless the budget says otherwise, step count capped at 5."""
+    sys.path.insert(0, str(ROOT))
+    import json
+    import types
+
+    import bench
+
+    for name in bench.WORKLOADS:
+        s = bench.workload_string(name)
+        assert s.startswith(name + ": ") and f"{bench.WORKLOADS[name][2]} views at {bench.WORKLOADS[name][3]}x{bench.WORKLOADS[name][3]}" in s
+    cb = bench.cpu_baseline("cube_w_hole", budget_s=0.3)
+    assert cb["gsamples_per_s"] > 0 and cb["kind"] == "port" and cb["cores"] >= 1 and "central rows" in cb["sample"]
+    orig = bench.cpu_baseline
+    calls = []
+
+    def fake(workload, budget_s=15.0, nthreads=0, volume=None):
+        calls.append(budget_s)
+        return {"gsamples_per_s": 0.5, "rays_per_s": 1000.0, "cores": 4, "kind": "port", "sample": "fake", "seconds": budget_s}
+
+    bench.cpu_baseline = fake
+    try:
+        bench.run_reference(types.SimpleNamespace(steps=20, warmup=3, cpu_budget=15.0, workload="lattice", gpus=1, volume_n=1024), 0, 1)
+    finally:
+        bench.cpu_baseline = orig
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 5 and line["steps_requested"] == 20
+    assert line["config"]["workload"] == bench.workload_string("lattice")
+    assert line["e2e"] == {"value": line["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert all(b >= 3.0 for b in calls[1:])   # every timed step is a >= 3 s sample (calls[0] is the warm-up)
+    assert line["cpu_baseline"]["kind"] == "port" and line["metric"] == "Gsamples/s" and line["higher_is_better"] is True

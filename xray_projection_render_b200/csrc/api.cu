@@ -218,8 +218,19 @@ static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int 
 static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const void* borrowed_vox, DevScene** out,
                             int peer_dev = -1) {
     SceneCache* c = cache_of(sc);
-    std::lock_guard<std::mutex> lk(c->mu);
-    DevScene& ds = c->per_dev[dev];
+    // The lock covers the map only (its nodes are stable): one thread works on one device's entry, and a peer's entry is
+    // read-only while others pull from it, so the copies of different devices run side by side (tree replication below).
+    DevScene* dsp = nullptr;
+    const DevScene* peer_ds = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        dsp = &c->per_dev[dev];
+        if (peer_dev >= 0 && peer_dev != dev) {
+            auto it = c->per_dev.find(peer_dev);
+            if (it != c->per_dev.end()) peer_ds = &it->second;
+        }
+    }
+    DevScene& ds = *dsp;
     const Header* h = (const Header*)sc->blob.data();
     if (ds.dev < 0) {
         ds.dev = dev;
@@ -250,12 +261,7 @@ static int ensure_dev_scene(XRayScene* sc, int dev, cudaStream_t stream, const v
                 ds.vox_borrowed[s] = false;
                 if (!ds.d_vox[s]) CU(3, cudaMalloc(&ds.d_vox[s], bytes));
                 const DevScene* src = nullptr;
-                if (peer_dev >= 0 && peer_dev != dev) {
-                    auto it = c->per_dev.find(peer_dev);
-                    if (it != c->per_dev.end() && it->second.d_vox[s] && it->second.vox_version[s] == vh.version &&
-                        it->second.vox_bytes[s] == bytes)
-                        src = &it->second;
-                }
+                if (peer_ds && peer_ds->d_vox[s] && peer_ds->vox_version[s] == vh.version && peer_ds->vox_bytes[s] == bytes) src = peer_ds;
                 if (src) CU(4, cudaMemcpyPeerAsync(ds.d_vox[s], dev, src->d_vox[s], peer_dev, bytes, stream));
                 else CU(4, upload_h2d(ds.d_vox[s], vh.data, bytes, dev, stream));
                 ds.vox_bytes[s] = bytes;
@@ -1085,8 +1091,25 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
             cudaSetDevice(cur);
             return rc;
         }
-        replicated_from = devs[0];
+        // Binomial tree over NVLink / NVSwitch: in round r the 2^r devices that hold the volume each feed one that does not,
+        // so G devices are served in ceil(log2 G) copy times instead of G - 1 pulls from the one root.
+        std::vector<int> tree_rc(G, 0);
+        std::vector<std::string> tree_err(G);
+        for (int span = 1; span < G; span <<= 1) {
+            std::vector<std::thread> th;
+            for (int i = span; i < std::min(2 * span, G); ++i)
+                th.emplace_back([&, i, span]() {
+                    cudaSetDevice(devs[i]);
+                    DevScene* dsi = nullptr;
+                    tree_rc[i] = ensure_dev_scene(scene, devs[i], 0, nullptr, &dsi, devs[i - span]);
+                    if (tree_rc[i]) tree_err[i] = g_last_error;
+                });
+            for (auto& t : th) t.join();
+        }
         cudaSetDevice(cur);
+        for (int i = 1; i < G; ++i)
+            if (tree_rc[i]) return fail(tree_rc[i], tree_err[i]);
+        replicated_from = devs[0];  // (every device already holds the current version: the jobs find nothing left to copy)
     }
 
     // group views by R (the sample lattice depends on R), then shard each group modulo G
