@@ -1,7 +1,9 @@
-tools/ncu_span.sh lattice.json 1024 64 r2c_lattice render_span_kernel
-tools/ncu_span.sh pillar_array.json 4096 8 r2c_pillar render_span_kernel
-tools/ncu_span.sh gyroid_example.json 1024 64 r2c_gyroid render_async_kernel deformation_sigmoid.json
-tools/ncu_span.sh voxel1024 2048 8 r2c_voxel render_volume_tex_kernel
-tools/ncu_span.sh cube_w_hole.json 512 1 r2c_cube render_span_kernel
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-configs > gpurun_out/b_ncu.log 2>&1
-ls gpurun_out | grep r2c | head -40
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o /tmp/tma_probe tools/experiments/tma_brick_probe.cu && /tmp/tma_probe | tee gpurun_out/tma_brick_probe_r2.txt
+cuobjdump -sass /tmp/tma_probe | grep -c UTMALDG | sed 's/^/UTMALDG instructions in the probe SASS: /' | tee -a gpurun_out/tma_brick_probe_r2.txt
+python bench.py --workload voxel1024 --views 8 --no-configs --no-cpu --no-ref-cuda --steps 3 --warmup 3 > gpurun_out/bench_vox_skip.json 2>/dev/null
+XRAY_VOLUME_NO_SKIP=1 python bench.py --workload voxel1024 --views 8 --no-configs --no-cpu --no-ref-cuda --steps 3 --warmup 3 > gpurun_out/bench_vox_noskip.json 2>/dev/null
+python -c "
+import json
+for f in ('skip','noskip'):
+    d=json.load(open('gpurun_out/bench_vox_%s.json'%f)); print(f, 'value', d['value'], 'ms/step', d['ms_per_step'], 'evaluated', d['work_per_step']['intervals_or_evaluated_samples'], 'ref', d['work_per_step']['ref_samples'])
+" | tee -a gpurun_out/tma_brick_probe_r2.txt
