@@ -104,7 +104,9 @@ typedef struct {
                                   [3] primitive tests executed       [4] rays
                                   [5] kernel launches
                                   [6] image tiles the interval renderer handed to the marching kernels
-                                  [7] why (OR of reason bits, render_span.cu); bit 16 = the interval renderer ran */
+                                  [7] why (OR of reason bits, render_span.cu); bit 16 = the interval renderer ran;
+                                      bits 17 / 18 = density() > 0 at smin / smax for some ray (hierarchical integrator: the
+                                      reference's "Clipping at smin/smax detected" warnings, main.go:162-169) */
     int32_t view_begin;        /* first camera's global view index (for sharding bookkeeping only) */
     int32_t reserved[7];
 } XRayRenderOpts;

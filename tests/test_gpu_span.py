@@ -65,14 +65,20 @@ def test_tangent_and_axis_parallel_rays(X, O):
 
 
 def test_more_intervals_than_the_lists_hold(X, O):
-    """60 thin plates in a row: rays along the row cross far more intervals than the per-ray lists of the interval renderer
-    hold; those tiles go to the marching kernels (marched_tiles > 0) and the image is still exact."""
+    """60 thin plates in a row: rays along the row cross more intervals than the per-ray lists of the interval renderer hold.
+    With screen-space bins the settle pass renders such rays in windows of the lattice (sweep state carried across windows);
+    under a warp (no bins: each ray walks the candidate grid) those tiles go to the marching kernels.  Exact either way."""
     plates = [{"type": "box", "center": [-0.885 + 0.03 * k, 0.0, 0.0], "sides": [0.012, 0.8, 0.8], "rho": 0.05 + 0.01 * (k % 7)}
               for k in range(60)]
     obj = {"type": "object_collection", "objects": plates}
-    out, nref, _ = gpu_vs_oracle(X, O, obj, views=((0.0, 90.0), (60.0, 80.0)), res=48, ds=0.004)
-    assert_parity(out, nref)
-    assert out["fp32"][1]["marched_tiles"] > 0
+    for integ in ("hierarchical", "simple"):
+        out, nref, _ = gpu_vs_oracle(X, O, obj, views=((0.0, 90.0), (60.0, 80.0)), res=48, ds=0.004, integ=integ)
+        assert_parity(out, nref)
+        assert out["fp32"][1]["marched_tiles"] == 0 and out["fp32"][1]["span_renderer"]
+        out, nref, _ = gpu_vs_oracle(X, O, obj, {"type": "rigid", "displacements": [0.0, 0.01, 0.0]}, views=((0.0, 90.0), (60.0, 80.0)),
+                                     res=48, ds=0.004, integ=integ)
+        assert_parity(out, nref)
+        assert out["fp32"][1]["marched_tiles"] > 0
 
 
 def test_every_period_boundary_direction(X, O):
@@ -111,3 +117,39 @@ def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkey
         assert sa["ref_samples"] == sb["ref_samples"]
         assert sa["launches"] == 2 and sb["launches"] == 1
         assert sa["marched_tiles"] <= 0.002 * 2 * (res // 4) * (res // 8), sa  # warp tiles of 4 x 8 pixels
+
+
+def test_clipping_flags_match_the_reference_probes(X, O, monkeypatch):
+    """main.go:162-169: integrate_hierarchical evaluates density() at smin and smax of every ray and warns when it is > 0.
+    The library reports the same two facts in the stats (bits of stats[7]), for the interval renderer and the marching kernels."""
+    rod = {"type": "cylinder", "p0": [-2.5, 0.0, 0.1], "p1": [2.5, 0.0, 0.1], "radius": 0.15, "rho": 0.2}       # sticks out both ends
+    half = {"type": "cylinder", "p0": [0.0, 0.0, 0.1], "p1": [2.5, 0.0, 0.1], "radius": 0.15, "rho": 0.2}       # only on the +x side
+    ball = {"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.5, "rho": 1.0}
+    R_, res, ds = 4.0, 16, 0.02
+    for obj, view, want in ((rod, (0.0, 90.0), (True, True)), (half, (0.0, 90.0), (True, False)), (half, (180.0, 90.0), (False, True)),
+                            (ball, (0.0, 90.0), (False, False)), (rod, (90.0, 90.0), (False, False))):
+        sc = X.Scene({"type": "object_collection", "objects": [obj]})
+        cams = X.cameras_from_angles([view], R_, FOV)
+        for nospan in (False, True):
+            if nospan:
+                monkeypatch.setenv("XRAY_NO_SPAN", "1")
+            else:
+                monkeypatch.delenv("XRAY_NO_SPAN", raising=False)
+            _, st = X.render_scene(sc, cams, res, ds=ds, return_stats=True)
+            assert (st["clipping_smin"], st["clipping_smax"]) == want, (obj, view, st)
+            assert st["span_renderer"] == (not nospan)
+        monkeypatch.delenv("XRAY_NO_SPAN", raising=False)
+        # the oracle's own density() at the two ends of every ray
+        osc = O.OracleScene({"type": "object_collection", "objects": [obj]})
+        eye, cm = O.camera_from_angles(view[0], view[1], R_)
+        f = 1.0 / np.tan(np.deg2rad(FOV) / 2.0)
+        got = [False, False]
+        for i in range(res):
+            for j in range(res):
+                v = cm @ np.array([i / (res / 2) - 1, j / (res / 2) - 1, -f, 1.0])
+                d = v[:3] / v[3] - eye
+                d = d * (1.0 / np.sqrt(d @ d))
+                for e, s in enumerate((R_ - 1.74, R_ + 1.74)):
+                    p = eye + d * s
+                    got[e] = got[e] or osc.density(*p) > 0
+        assert tuple(got) == want

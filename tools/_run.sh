@@ -1,9 +1,3 @@
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o /tmp/tma_probe tools/experiments/tma_brick_probe.cu && /tmp/tma_probe | tee gpurun_out/tma_brick_probe_r2.txt
-cuobjdump -sass /tmp/tma_probe | grep -c UTMALDG | sed 's/^/UTMALDG instructions in the probe SASS: /' | tee -a gpurun_out/tma_brick_probe_r2.txt
-python bench.py --workload voxel1024 --views 8 --no-configs --no-cpu --no-ref-cuda --steps 3 --warmup 3 > gpurun_out/bench_vox_skip.json 2>/dev/null
-XRAY_VOLUME_NO_SKIP=1 python bench.py --workload voxel1024 --views 8 --no-configs --no-cpu --no-ref-cuda --steps 3 --warmup 3 > gpurun_out/bench_vox_noskip.json 2>/dev/null
-python -c "
-import json
-for f in ('skip','noskip'):
-    d=json.load(open('gpurun_out/bench_vox_%s.json'%f)); print(f, 'value', d['value'], 'ms/step', d['ms_per_step'], 'evaluated', d['work_per_step']['intervals_or_evaluated_samples'], 'ref', d['work_per_step']['ref_samples'])
-" | tee -a gpurun_out/tma_brick_probe_r2.txt
+python tools/span_reasons.py 2>&1 | grep -v simple | grep lattice | tee gpurun_out/span_reasons6.txt
+timeout 1700 python -m pytest tests/test_gpu_span.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_properties.py -x -q -m gpu 2>&1 | tail -12
+python tools/span_time.py lattice pillar cube 2>&1 | tee gpurun_out/span_time12.txt

@@ -15,5 +15,5 @@ for name, res, views in (("cube_w_hole", 40, [(77.0, 83.0)]), ("cube_w_hole", 40
     cams = X.cameras_from_angles(views, 4.0, 40.0)
     for integ in ("hierarchical", "simple"):
         _, st = X.render_scene(sc, cams, res, integration=integ, return_stats=True)
-        print(f"{name:14s} res {res:5d} view {views[0]} {integ:12s}: marched_tiles {st['marched_tiles']:5d} of {((res + 7) // 8) * ((res + 15) // 16)} reasons {st['march_reasons'] & 0xffff:#x} "
+        print(f"{name:14s} res {res:5d} view {views[0]} {integ:12s}: marched_tiles {st['marched_tiles']:5d} of {((res + 7) // 8) * ((res + 15) // 16)} reasons {st['march_reasons']:#x} "
               f"fallbacks {st['fp64_fallbacks']}", flush=True)

@@ -29,6 +29,7 @@
 namespace xr {
 cudaError_t launch_render_scene(const RenderParams& P, int precision, int integrator, cudaStream_t stream);
 cudaError_t launch_voxelize_scene(const RenderParams& P, int res, float* d_out, cudaStream_t stream);
+cudaError_t launch_clip_probe(const RenderParams& P, cudaStream_t stream);
 cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream);
 cudaError_t launch_render_fast(const RenderParams& P, int shape, int integrator, bool count, bool list, int prim,
                                const unsigned char* d_nfine, int i_coll, int i_tess, cudaStream_t stream);
@@ -765,7 +766,7 @@ static int run_job(Job& J) {
             }
             C->tile_list_cap = 0;
             for (int b = 0; b < 2; ++b)
-                CUJ(3, cudaMalloc(&C->d_tile_list[b], (need + 2) * sizeof(unsigned int)));  // [0] = count, [1] = work counter, [2..] = ids
+                CUJ(3, cudaMalloc(&C->d_tile_list[b], (2 * need + 2) * sizeof(unsigned int)));  // [0], [1] = counts; hand-over ids; settle-pass ids
             C->tile_list_cap = need;
         }
     }
@@ -797,8 +798,13 @@ static int run_job(Job& J) {
         }
         if (ok) {
             n_instances = sh->n_periods * sh->n_children;
-            bin_cap = std::min<unsigned int>(64u, n_instances);
-            const size_t words = (size_t)max_batch * P.tiles_i * P.tiles_j * (1 + (size_t)bin_cap);
+            // 128 entries per tile when that stays under 1 GiB (a tile on a row of lattice nodes, seen edge-on, lists ~100), else 64
+            bin_cap = std::min<unsigned int>(128u, n_instances);
+            size_t words = (size_t)max_batch * P.tiles_i * P.tiles_j * (1 + (size_t)bin_cap);
+            if (words * sizeof(unsigned int) > ((size_t)1 << 30)) {
+                bin_cap = std::min<unsigned int>(64u, n_instances);
+                words = (size_t)max_batch * P.tiles_i * P.tiles_j * (1 + (size_t)bin_cap);
+            }
             if (words * sizeof(unsigned int) > ((size_t)1 << 30)) bin_cap = 0;  // never more than 1 GiB of bins
             else if (words > C->bins_cap_words) {
                 CUJ(7, cudaStreamSynchronize(stream));
@@ -839,6 +845,18 @@ static int run_job(Job& J) {
         P.tile_count = nullptr;
         // the grid is one CTA per (view, tile); keep it below 2^31
         if ((size_t)n * P.tiles_i * P.tiles_j > 0x7fffffffull) return cudaErrorInvalidValue;
+        if (P.stats && J.opts.integration == XRAY_INTEGRATE_HIERARCHICAL) {  // main.go:162-169 clipping warnings, as stats[7] bits 17 / 18
+            const int smem_flag = P.prog_in_smem;
+            const unsigned int smem_bytes = P.smem_prog_bytes;
+            if (use_list) {  // (list scenes stage only the instructions for the fast kernels; the probe reads everything from global)
+                P.prog_in_smem = 0;
+                P.smem_prog_bytes = 0;
+            }
+            cudaError_t ec = launch_clip_probe(P, stream);
+            P.prog_in_smem = smem_flag;
+            P.smem_prog_bytes = smem_bytes;
+            if (ec != cudaSuccess) return ec;
+        }
         if (!use_span) return launch_march(stream);
         unsigned int* tl = C->d_tile_list[parity];
         cudaError_t es = launch_render_span(P, J.opts.integration, P.stats != nullptr, C->d_nfine, ds->d_blob + h->span_off, h->span_bytes,
@@ -1152,11 +1170,17 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
         cudaSetDevice(cur_dev);
         for (int g = 0; g < G; ++g) {
             if (jobs[g].rc) return fail(jobs[g].rc, jobs[g].err);
-            for (int s = 0; s < XRAY_NUM_STATS; ++s) stats_total[s] += jobs[g].stats[s];
+            for (int s = 0; s < XRAY_NUM_STATS; ++s) {
+                if (s == 7) stats_total[s] |= jobs[g].stats[s];  // a bit set, not a counter
+                else stats_total[s] += jobs[g].stats[s];
+            }
         }
     }
     if (opts.stats)
-        for (int s = 0; s < XRAY_NUM_STATS; ++s) opts.stats[s] += stats_total[s];
+        for (int s = 0; s < XRAY_NUM_STATS; ++s) {
+            if (s == 7) opts.stats[s] |= stats_total[s];
+            else opts.stats[s] += stats_total[s];
+        }
     return 0;
 }
 

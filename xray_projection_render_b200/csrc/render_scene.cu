@@ -268,8 +268,47 @@ __global__ void __launch_bounds__(kBlockThreads) voxelize_scene_kernel(const Ren
 }
 
 // ---------------------------------------------------------------------------------------
+// Clipping probe (main.go:162-169): the hierarchical integrator evaluates density() at smin and smax of every ray
+// and warns once when the object sticks out of the sample window.  Here: the same two exact evaluations per ray, OR-ed
+// into stats[7] (bit 17: density > 0 at smin for some ray, bit 18: at smax).  Runs only when the caller asked for stats.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlockThreads) clip_probe_kernel(const RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SceneView S = stage_program(P, smem);
+    SaveStack<Exact> st;
+    st.r = reinterpret_cast<double*>(smem + P.smem_prog_bytes);
+    st.u = reinterpret_cast<unsigned int*>(st.r + (size_t)P.scene.save_depth * 5 * blockDim.x);
+    int view, i, j;
+    pixel_of_thread(P, blockIdx.x, threadIdx.x >> 5, view, i, j);
+    const bool valid = i < P.res && j < P.res;
+    const Ray64 ray = make_ray(P.cams[view], valid ? i : 0, valid ? j : 0, P.res);
+    unsigned int bits = 0u;
+#pragma unroll 1
+    for (int e = 0; e < 2; ++e) {
+        const double s = e ? P.smax : P.smin;
+        const double x = dadd(ray.o[0], dmul(ray.d[0], s)), y = dadd(ray.o[1], dmul(ray.d[1], s)), z = dadd(ray.o[2], dmul(ray.d[2], s));
+        Counters cnt = {0};
+        bool dummy = false;
+        const double rho = dmul(eval_scene<Exact>(S, x, y, z, valid, dummy, st, cnt), P.dm);
+        if (valid && rho > 0.0) bits |= 1u << (17 + e);
+    }
+    bits = __reduce_or_sync(FULL_MASK, bits);
+    if ((threadIdx.x & 31) == 0 && bits && P.stats) atomicOr(P.stats + 7, (unsigned long long)bits);
+}
+
+// ---------------------------------------------------------------------------------------
 // Launchers (called from api.cu)
 // ---------------------------------------------------------------------------------------
+cudaError_t launch_clip_probe(const RenderParams& P, cudaStream_t stream) {
+    size_t smem = P.smem_prog_bytes + (size_t)P.scene.save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));
+    const unsigned int grid = (unsigned int)((size_t)P.n_views * P.tiles_i * P.tiles_j);
+    if (grid == 0 || !P.stats) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(clip_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    clip_probe_kernel<<<grid, kBlockThreads, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
 size_t scene_kernel_smem_bytes(const RenderParams& P, bool with_queue) {
     size_t b = P.smem_prog_bytes;
     b += (size_t)P.scene.save_depth * kBlockThreads * (5 * sizeof(double) + 4 * sizeof(unsigned int));

@@ -25,27 +25,21 @@ namespace xr {
 #ifndef XR_SPAN_MINBLOCKS
 #define XR_SPAN_MINBLOCKS 4
 #endif
-#ifndef XR_SPAN_PERSISTENT
-#define XR_SPAN_PERSISTENT 0
-#endif
-#if XR_SPAN_PERSISTENT
-#define XR_SPAN_NEXT continue
-#else
-#define XR_SPAN_NEXT return
-#endif
 #ifndef XR_SPAN_CAPMAX
 #define XR_SPAN_CAPMAX 64
 #endif
 // Per-ray list capacity (candidates that survive the pre-filter = intervals at most): whatever fits the shared memory a CTA may
 // use at XR_SPAN_MINBLOCKS CTAs per SM, at most 64.
 constexpr int kSpanCapMax = XR_SPAN_CAPMAX;
+constexpr int kSpanFuzzCap = 4;  // candidates per ray set aside for exact settling
 constexpr double kZone = 1.0e-11; // half-width (in s) of the doubt zone around every end point
 
 struct SpanArgs {
     const unsigned char* section;  // device copy of the SpanHeader section
     unsigned int section_bytes;
     unsigned int* tile_list;       // out: warp tiles ((view, tile) id * 4 + warp position) with a ray that needs the marching kernels
-    unsigned int* tile_count;      // out: their number (zeroed before the launch); tile_count[1] = the work counter of the launch
+    unsigned int* tile_count;      // out: [0] their number, [1] the number of settle_list entries (both zeroed before the launch)
+    unsigned int* settle_list;     // out (fast pass) / in (settle pass): warp tiles whose only doubt is a lattice sample inside a doubt zone
     unsigned int total_items;      // warp tiles of the launch = views * tiles * 4
     int cap;                       // per-ray list capacity
     // screen-space bins (span_bin_kernel): per (view, tile) the (period, child) instances whose projection meets the tile
@@ -54,19 +48,21 @@ struct SpanArgs {
     unsigned int bin_cap;
 };
 
-static int span_list_cap(unsigned int section_bytes) {
+static int span_list_cap(unsigned int section_bytes, bool with_fuzz) {
     const size_t budget = (size_t)216 * 1024 / XR_SPAN_MINBLOCKS - 1024;  // 228 KB per SM, 1 KB per CTA reserved, some slack
     const size_t sec = (section_bytes + 15u) & ~15u;
-    if (budget < sec + (size_t)8 * kBlockThreads * 8) return 0;
-    const size_t cap = (budget - sec) / ((size_t)kBlockThreads * 8);
+    const size_t fz = with_fuzz ? (size_t)kSpanFuzzCap * kBlockThreads * 4 : 0;
+    if (budget < sec + fz + (size_t)8 * kBlockThreads * 8) return 0;
+    const size_t cap = (budget - sec - fz) / ((size_t)kBlockThreads * 8);
     return (int)(cap < (size_t)kSpanCapMax ? cap : (size_t)kSpanCapMax);
 }
 
-size_t span_kernel_smem_bytes(unsigned int section_bytes) {
-    const int cap = span_list_cap(section_bytes);
+static size_t span_smem_bytes(unsigned int section_bytes, bool with_fuzz) {
+    const int cap = span_list_cap(section_bytes, with_fuzz);
     if (cap <= 0) return (size_t)1 << 30;  // does not fit: the caller keeps to the marching kernels
-    return (size_t)((section_bytes + 15u) & ~15u) + (size_t)cap * kBlockThreads * 8;
+    return (size_t)((section_bytes + 15u) & ~15u) + (size_t)cap * kBlockThreads * 8 + (with_fuzz ? (size_t)kSpanFuzzCap * kBlockThreads * 4 : 0);
 }
+size_t span_kernel_smem_bytes(unsigned int section_bytes) { return span_smem_bytes(section_bytes, true); }
 
 // The set of ray parameters that satisfy every constraint seen so far is an interval whose ends are known up to a
 // doubt zone each:  t > L1 surely passes every lower bound, t < L0 surely fails one;  t < U0 surely passes every upper
@@ -116,6 +112,59 @@ __device__ __forceinline__ bool span_quadratic(double A, double B, double C, Spa
     return r.L0 <= r.U1;
 }
 
+// The ray in object space, centred on the window (x(t) = c + d t, t = s - R), with what the slabs need.
+struct SpanRay {
+    double cx, cy, cz, dx, dy, dz, jdx, jdy, jdz, epsx;
+};
+
+// Parameter range of the ray inside child K of period (px, py, pz), intersected with R0 (the outer box): three period
+// slabs (not along a degenerate axis, whose period is settled per ordinal), then the primitive.
+__device__ __forceinline__ bool span_candidate_range(const SpanHeader& H, const SpanChild& K, const SpanRay& y, const SpanRange& R0, int px, int py,
+                                                     int pz, int deg_axis, SpanRange& r, unsigned int& doubt) {
+    const double dx = y.dx, dy = y.dy, dz = y.dz, epsx = y.epsx;
+    // ray centre in the coordinates of this period: x' = x - dx * n (objects.go:571)
+    const double ux = y.cx - H.uc_d[0] * (double)px, uy = y.cy - H.uc_d[1] * (double)py, uz = y.cz - H.uc_d[2] * (double)pz;
+    r = R0;
+    bool ok = true;
+    if (H.flags & SPAN_TESS) {  // the period's own cell: floor((x - min) / d) == n  <=>  min <= x' < min + d
+        if (deg_axis != 0) ok = ok && span_slab(ux, dx, y.jdx, H.uc_lo[0], H.uc_lo[0] + H.uc_d[0], epsx, r, doubt);
+        if (deg_axis != 1) ok = ok && span_slab(uy, dy, y.jdy, H.uc_lo[1], H.uc_lo[1] + H.uc_d[1], epsx, r, doubt);
+        if (deg_axis != 2) ok = ok && span_slab(uz, dz, y.jdz, H.uc_lo[2], H.uc_lo[2] + H.uc_d[2], epsx, r, doubt);
+    }
+    if (!ok) return false;
+    const double* p = K.p;
+    if (K.type == OP_CYL || K.type == OP_SPHERE) {
+        const double wx = ux - p[0], wy = uy - p[1], wz = uz - p[2];
+        double A = dx * dx + dy * dy + dz * dz, B = wx * dx + wy * dy + wz * dz, C = wx * wx + wy * wy + wz * wz;
+        if (K.type == OP_CYL) {
+            const double dv = dx * p[3] + dy * p[4] + dz * p[5], wv = wx * p[3] + wy * p[4] + wz * p[5], ivv = p[6];
+            A -= dv * dv * ivv;
+            B -= wv * dv * ivv;
+            C -= wv * wv * ivv;
+            C -= p[7];
+            // caps: 0 <= (w.v + t d.v) / v.v <= 1, inclusive (objects.go:339-341)
+            const double cd = dv * ivv;
+            ok = span_slab(wv * ivv, cd, 1.0 / cd, 0.0, 1.0, 1.0e-13, r, doubt);
+        } else {
+            C -= p[3];
+        }
+        ok = ok && span_quadratic(fmax(A, 0.0), B, C, r, doubt);
+    } else if (K.type == OP_BOX) {
+        ok = ok && span_slab(ux, dx, y.jdx, p[0] - p[3], p[0] + p[3], epsx, r, doubt);
+        ok = ok && span_slab(uy, dy, y.jdy, p[1] - p[4], p[1] + p[4], epsx, r, doubt);
+        ok = ok && span_slab(uz, dz, y.jdz, p[2] - p[5], p[2] + p[5], epsx, r, doubt);
+    } else {  // parallelepiped: 0 < Minv (x - o) < 1 per component (objects.go:249-254)
+        const double wx = ux - p[0], wy = uy - p[1], wz = uz - p[2];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            const double q0 = p[3 + 3 * rr] * wx + p[4 + 3 * rr] * wy + p[5 + 3 * rr] * wz;
+            const double qd = p[3 + 3 * rr] * dx + p[4 + 3 * rr] * dy + p[5 + 3 * rr] * dz;
+            ok = ok && span_slab(q0, qd, 1.0 / qd, 0.0, 1.0, epsx * (1.0 + p[12 + rr]), r, doubt);
+        }
+    }
+    return ok;
+}
+
 // Smallest lattice ordinal whose position is > s; doubt when a lattice position lies within zw of s.
 //   simple integrator:       ordinal k        <-> s_tab[k],                 k in [0, n)
 //   hierarchical integrator: ordinal 16 k + j <-> s_tab[k] + j * ds_fine    (j = 1 .. nfine[k], main.go:183-189)
@@ -162,6 +211,127 @@ __device__ __forceinline__ unsigned int span_ordinal_after(const RenderParams& P
     if (fabs(r - rint(r)) * P.ds_fine < zw || right - s < zw) doubt |= 4u;
     const int j0 = (int)r + 1;
     return 16u * (unsigned int)k + (j0 > nf ? 15u : (unsigned int)j0);
+}
+
+// Exact position of a lattice ordinal, as the reference's loops produce it (repeated addition, main.go:147,183-189).
+template <int INTEG>
+__device__ __forceinline__ double span_exact_pos(const RenderParams& P, const unsigned char* __restrict__ nfine, unsigned int e) {
+    if (INTEG == 0) return __ldg(P.s_tab + e);
+    const unsigned int k = e >> 4, j = e & 15u;
+    const unsigned int nf = (unsigned int)__ldg(nfine + k);
+    if (j == 0u || j > nf) return __ldg(P.s_tab + k + (j == 0u ? 0u : 1u));  // not a fine sample: the neighbouring coarse one
+    double s = __ldg(P.s_tab + k);
+    for (unsigned int q = 0; q < j; ++q) s = dadd(s, P.ds_fine);
+    return s;
+}
+
+template <int INTEG>
+__device__ __forceinline__ unsigned int span_next_ordinal(const unsigned char* __restrict__ nfine, unsigned int e) {
+    if (INTEG == 0) return e + 1u;
+    const unsigned int k = e >> 4, j = e & 15u;
+    if (j == 15u) return 16u * (k + 1u) + 1u;
+    return j < (unsigned int)__ldg(nfine + k) ? e + 1u : 16u * k + 15u;
+}
+
+// Does the reference see lattice sample e of this ray inside child K of period (px, py, pz)?  The reference's own
+// expressions in its own operation order (no FMA): position main.go:147-149, outer bounds / fold / unit-cell bounds
+// objects.go:568-582, 458-464, primitive tests objects.go:63-72, 171-179, 247-255, 334-350.  Cold: only lattice samples
+// that fall inside the doubt zone of an interval end point come here (un-warped scenes).
+template <int INTEG>
+__device__ __forceinline__ bool span_exact_member(const RenderParams& P, const unsigned char* __restrict__ nfine, const SpanHeader* H,
+                                               const SpanChild* K, const double* __restrict__ eye, double dx, double dy, double dz,
+                                               unsigned int e, int px, int py, int pz) {
+    const double s = span_exact_pos<INTEG>(P, nfine, e);
+    double x = dadd(eye[0], dmul(dx, s)), y = dadd(eye[1], dmul(dy, s)), z = dadd(eye[2], dmul(dz, s));
+    if (H->flags & SPAN_TESS) {
+        const double* o = H->outer;
+        if (x < o[0] || x > o[3] || y < o[1] || y > o[4] || z < o[2] || z > o[5]) return false;
+        const double nx = floor(ddiv(dsub(x, H->uc_lo[0]), H->uc_d[0])), ny = floor(ddiv(dsub(y, H->uc_lo[1]), H->uc_d[1])),
+                     nz = floor(ddiv(dsub(z, H->uc_lo[2]), H->uc_d[2]));
+        if ((int)nx != px || (int)ny != py || (int)nz != pz) return false;
+        x = dsub(x, dmul(H->uc_d[0], nx));
+        y = dsub(y, dmul(H->uc_d[1], ny));
+        z = dsub(z, dmul(H->uc_d[2], nz));
+        if (x < H->uc_lo[0] || x > H->uc_hi[0] || y < H->uc_lo[1] || y > H->uc_hi[1] || z < H->uc_lo[2] || z > H->uc_hi[2]) return false;
+    }
+    const double* p = K->p;
+    if (K->type == OP_SPHERE) {
+        const double ax = dsub(x, p[0]), ay = dsub(y, p[1]), az = dsub(z, p[2]);
+        return dadd(dadd(dmul(ax, ax), dmul(ay, ay)), dmul(az, az)) < p[3];
+    }
+    if (K->type == OP_BOX) return fabs(dsub(x, p[0])) < p[3] && fabs(dsub(y, p[1])) < p[4] && fabs(dsub(z, p[2])) < p[5];
+    if (K->type == OP_CYL) {
+        const double wx = dsub(x, p[0]), wy = dsub(y, p[1]), wz = dsub(z, p[2]);
+        const double wv = dadd(dadd(dmul(wx, p[3]), dmul(wy, p[4])), dmul(wz, p[5]));
+        const double cc = ddiv(wv, p[8]);
+        if (cc < 0.0 || cc > 1.0) return false;
+        const double ex = dsub(wx, dmul(p[3], cc)), ey = dsub(wy, dmul(p[4], cc)), ez = dsub(wz, dmul(p[5], cc));
+        return __dsqrt_rn(dadd(dadd(dmul(ex, ex), dmul(ey, ey)), dmul(ez, ez))) < p[9];
+    }
+    const double ax = dsub(x, p[0]), ay = dsub(y, p[1]), az = dsub(z, p[2]);
+    const double qx = dadd(dadd(dmul(p[3], ax), dmul(p[4], ay)), dmul(p[5], az));
+    const double qy = dadd(dadd(dmul(p[6], ax), dmul(p[7], ay)), dmul(p[8], az));
+    const double qz = dadd(dadd(dmul(p[9], ax), dmul(p[10], ay)), dmul(p[11], az));
+    return qx > 0.0 && qx < 1.0 && qy > 0.0 && qy < 1.0 && qz > 0.0 && qz < 1.0;
+}
+
+// Settle the lattice samples that lie inside the doubt zone of an interval's end point(s) one by one with the reference's own
+// expressions: by convexity the first member from the lower side and the first non-member after it fix [e_in, e_out).
+// Cold and out of line (called after the hot loop for the few candidates it set aside): recomputes the candidate's range.
+// Returns doubt bits (0 = settled; e_in >= e_out = no lattice sample inside).
+template <int INTEG>
+__device__ __noinline__ unsigned int span_settle(const RenderParams& P, const unsigned char* __restrict__ nfine, const SpanHeader* H,
+                                                 const SpanChild* ch, const double* __restrict__ eye, const SpanRay* ray, const SpanRange* R0,
+                                                 unsigned int code, int deg_axis, unsigned int e_last, unsigned int& e_in, unsigned int& e_out) {
+    const int c = (int)(code & 63u);
+    const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
+    const SpanChild* K = ch + c;
+    const double inv_ds = 1.0 / P.ds, inv_dsf = 1.0 / P.ds_fine;
+    SpanRange r;
+    unsigned int bits = 0u, near_lo = 0u, near_hi = 0u, dummy = 0u;
+    e_in = e_out = 0u;
+    if (!span_candidate_range(*H, *K, *ray, *R0, px, py, pz, deg_axis, r, bits)) return bits;
+    const double sc = P.s_center;
+    const bool sure = r.L1 <= r.U0;
+    if (sure) {
+        e_in = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.L1) + sc, 0.5 * (r.L1 - r.L0), inv_ds, inv_dsf, near_lo);
+        e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.U0 + r.U1) + sc, 0.5 * (r.U1 - r.U0), inv_ds, inv_dsf, near_hi);
+    } else {
+        e_in = e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.U1) + sc, 0.5 * (r.U1 - r.L0), inv_ds, inv_dsf, near_lo);
+        near_hi = near_lo;
+    }
+    const double dx = ray->dx, dy = ray->dy, dz = ray->dz;
+    if (near_lo) {
+        unsigned int e = span_ordinal_after<INTEG>(P, nfine, r.L0 + sc, 0.0, inv_ds, inv_dsf, dummy);  // first sample beyond L0
+        const double stop = (sure ? r.L1 : r.U1) + sc + 1.0e-13;
+        int guard = 0;
+        while (e < e_last && span_exact_pos<INTEG>(P, nfine, e) <= stop) {
+            if (span_exact_member<INTEG>(P, nfine, H, K, eye, dx, dy, dz, e, px, py, pz)) break;
+            e = span_next_ordinal<INTEG>(nfine, e);
+            if (++guard > 12) {
+                bits |= 4u;
+                break;
+            }
+        }
+        e_in = e;
+        if (!sure) e_out = e;  // (the upper loop starts here)
+    }
+    if (near_hi) {
+        unsigned int e = sure ? span_ordinal_after<INTEG>(P, nfine, r.U0 + sc, 0.0, inv_ds, inv_dsf, dummy) : e_out;
+        if (e < e_in) e = e_in;
+        const double stop = r.U1 + sc + 1.0e-13;
+        int guard = 0;
+        while (e < e_last && span_exact_pos<INTEG>(P, nfine, e) <= stop) {
+            if (!span_exact_member<INTEG>(P, nfine, H, K, eye, dx, dy, dz, e, px, py, pz)) break;
+            e = span_next_ordinal<INTEG>(nfine, e);
+            if (++guard > 12) {
+                bits |= 4u;
+                break;
+            }
+        }
+        e_out = e;
+    }
+    return bits;
 }
 
 // A ray that runs INSIDE a cell-face plane of a tessellation (the central pixel row at polar = 90 deg lies in z = 0): its
@@ -242,7 +412,11 @@ __device__ __forceinline__ double span_combine(const SpanChild* __restrict__ ch,
     return dmul(sum, dm);
 }
 
-template <int INTEG, bool COUNT>
+// SETTLE = false: the fast pass over every warp tile of the launch; a ray with a lattice sample inside a doubt zone only
+// flags its warp tile for the settle pass.  SETTLE = true: the same code over the flagged warp tiles, with the exact settling
+// of those samples compiled in (span_settle; it costs the hot loop 15 % in registers and stack traffic, so the fast pass
+// does not carry it).  Whatever neither pass can vouch for goes to the marching kernels.
+template <int INTEG, bool COUNT, bool SETTLE>
 __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_kernel(const RenderParams P, const unsigned char* __restrict__ nfine,
                                                                        const SpanArgs SA) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -253,7 +427,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         const int n16 = (int)((SA.section_bytes + 15u) >> 4);
         for (int k = tid; k < n16; k += kBlockThreads) dst[k] = __ldg(src + k);
     }
-    if (COUNT && P.stats && blockIdx.x == 0 && tid == 0) atomicOr(P.stats + 7, 0x10000ull);  // "the interval renderer ran"
+    if (!SETTLE && COUNT && P.stats && blockIdx.x == 0 && tid == 0) atomicOr(P.stats + 7, 0x10000ull);  // "the interval renderer ran"
     const SpanHeader& H = *reinterpret_cast<const SpanHeader*>(smem);
     unsigned int* cand = reinterpret_cast<unsigned int*>(smem + ((SA.section_bytes + 15u) & ~15u));
     // interval q is written after candidate q has been read and there are never more intervals than candidates read, so
@@ -261,29 +435,18 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
     unsigned int* iv_in = cand;
     const int cap = SA.cap;
     unsigned int* iv_out = cand + cap * kBlockThreads;
+    unsigned int* fuzz = iv_out + cap * kBlockThreads;  // settle pass only
     __syncthreads();
     const SpanChild* __restrict__ ch = reinterpret_cast<const SpanChild*>(smem + H.child_off);
     const unsigned long long* __restrict__ masks = reinterpret_cast<const unsigned long long*>(smem + H.mask_off);
     const unsigned int flags = H.flags;
     const bool tess = (flags & SPAN_TESS) != 0u;
 
-    // Persistent warps: every warp of the grid draws warp tiles (32 pixels, the same 4 x 8 footprint the marching kernels
-    // use) from a global counter, four at a time (= one CTA tile of the marching kernels), until none are left; rays differ
-    // a lot in cost (most miss the object), so a fixed assignment would leave warps idle.  Nothing below synchronises beyond
-    // the warp.
-#if XR_SPAN_PERSISTENT
-    constexpr unsigned int kChunk = 4;
-    for (;;) {
-    unsigned int base = 0u;
-    if ((tid & 31) == 0) base = atomicAdd(SA.tile_count + 1, kChunk);
-    base = __shfl_sync(FULL_MASK, base, 0);
-    if (base >= SA.total_items) break;
-    for (unsigned int item = base; item < min(base + kChunk, SA.total_items); ++item) {
-#else
-    {
-    {
-    const unsigned int item = blockIdx.x * (kBlockThreads / 32) + (tid >> 5);
-#endif
+    // One warp = one warp tile (32 pixels, the same 4 x 8 footprint the marching kernels use); nothing below synchronises
+    // beyond the warp.  The settle pass strides over its list.
+    const unsigned int n_items = SETTLE ? SA.tile_count[1] : SA.total_items;
+    for (unsigned int wi = blockIdx.x * (kBlockThreads / 32) + (tid >> 5); wi < n_items; wi = SETTLE ? wi + gridDim.x * (kBlockThreads / 32) : n_items) {
+    const unsigned int item = SETTLE ? SA.settle_list[wi] : wi;
     int view, i, j;
     pixel_of_thread(P, item >> 2, item & 3u, view, i, j);
     const bool valid = i < P.res && j < P.res;
@@ -397,11 +560,13 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         }
     };
     bool walk = hit;
+    unsigned int nb = 0u;                        // entries of this tile's bin (binned mode)
+    const unsigned int* __restrict__ bl = nullptr;
     if (SA.bin_counts) {  // uniform
-        const unsigned int nb = __ldg(SA.bin_counts + (item >> 2));
+        nb = __ldg(SA.bin_counts + (item >> 2));
         if (nb <= SA.bin_cap) {  // (a bin that overflowed is not used: those tiles walk)
             walk = false;
-            const unsigned int* __restrict__ bl = SA.bin_lists + (size_t)(item >> 2) * SA.bin_cap;
+            bl = SA.bin_lists + (size_t)(item >> 2) * SA.bin_cap;
             const float ucdx = (float)H.uc_d[0], ucdy = (float)H.uc_d[1], ucdz = (float)H.uc_d[2];
             const float ulx = H.f_uc_lo[0], uly = H.f_uc_lo[1], ulz = H.f_uc_lo[2];
             for (unsigned int q = 0; q < nb; ++q) {
@@ -515,26 +680,56 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             if (guard == 4095) overflow = true;
         }
     }
-    if (overflow) ncand = 0;
+    // More survivors than the list holds: with a bin at hand the ray simply takes every entry of the bin through the exact
+    // stage (no list needed); a walking ray is handed over.
+    // More survivors than the list holds: with a bin at hand the ray takes every entry of the bin through the exact stage
+    // instead (no list needed); a walking ray is handed over.
+    bool redo = overflow && bl != nullptr;
+    if (redo) overflow = false;
+    if (overflow || redo) ncand = 0;
 
     // ---- phase 2: exact interval of every surviving (period, child), mapped to lattice ordinals ----
     // (the reciprocals are recomputed here rather than kept alive across the walk: 6 registers for 3 divisions per ray)
-    const double jdx = 1.0 / dx, jdy = 1.0 / dy, jdz = 1.0 / dz;
+    const SpanRay ray = {cx, cy, cz, dx, dy, dz, 1.0 / dx, 1.0 / dy, 1.0 / dz, epsx};  // (its address is taken in the settle pass only)
     const unsigned int e_first = INTEG == 1 ? 1u : 0u;
     const unsigned int e_last = INTEG == 1 ? 16u * (unsigned int)P.n_steps : (unsigned int)P.n_steps;  // one past the last ordinal
-    int niv = 0;
     unsigned int prim_tests = 0;
-    const int max_cand = __reduce_max_sync(FULL_MASK, ncand);
+    double T = 0.0;
+    unsigned int n_fine = 0;
+    int niv = 0;
+    // A ray that crosses more primitives than its interval list holds (rays along a row of lattice nodes) is rendered in
+    // WINDOWS of the lattice: the settle pass retries with 2, 4, ... 16 windows (aligned to coarse intervals; the sweep's
+    // state -- zero-ness of the last coarse sample -- carries over), candidates straight from the tile's bin.  The fast
+    // pass makes one attempt with one window and flags the warp tile otherwise.
+    unsigned int n_win = 1u;
+    for (;;) {
+    T = 0.0;
+    n_fine = 0;
+    prim_tests = 0;
+    bool prev_z = false;  // prev_rho := 0.0 (main.go:179)
+    double facc = 0.0;    // sum of the fine samples seen so far in the coarse interval under way
+    bool ovf = overflow;
+    for (unsigned int win = 0; win < n_win; ++win) {
+    unsigned int win_lo = e_first, win_hi = e_last;
+    if (SETTLE && n_win > 1u) {
+        const unsigned int span_e = e_last - e_first;
+        win_lo = e_first + (unsigned int)(((unsigned long long)span_e * win) / n_win);
+        win_hi = e_first + (unsigned int)(((unsigned long long)span_e * (win + 1u)) / n_win);
+        if (INTEG == 1) {  // windows start on the first fine sample of a coarse interval: ordinals 16 k + 1
+            win_lo = ((win_lo - 1u) & ~15u) + 1u;
+            win_hi = win + 1u == n_win ? e_last : ((win_hi - 1u) & ~15u) + 1u;
+        }
+    }
+    niv = 0;
+    int nfz = 0;
+    const int my_cand = redo ? (int)nb : ncand;
+    const int max_cand = __reduce_max_sync(FULL_MASK, my_cand);
     for (int q = 0; q < max_cand; ++q) {
-        if (q >= ncand) continue;
-        const unsigned int code = cand[q * kBlockThreads + tid];
+        if (q >= my_cand) continue;
+        const unsigned int code = redo ? __ldg(bl + q) : cand[q * kBlockThreads + tid];
         const int c = (int)(code & 63u);
         const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
         if (COUNT) ++prim_tests;
-        // ray centre in the coordinates of this period: x' = x - dx * n (objects.go:571)
-        const double ux = cx - H.uc_d[0] * (double)px, uy = cy - H.uc_d[1] * (double)py, uz = cz - H.uc_d[2] * (double)pz;
-        SpanRange r = R0;
-        bool ok = true;
         unsigned int w_lo = e_first, w_hi = e_last;  // ordinal window of this period along a degenerate axis
         if (deg_axis >= 0) {
             const int pa = deg_axis == 0 ? px : (deg_axis == 1 ? py : pz);
@@ -548,77 +743,73 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
                 continue;
             }
         }
-        if (tess) {  // the period's own cell: floor((x - min) / d) == n  <=>  min <= x' < min + d
-            if (deg_axis != 0) ok = ok && span_slab(ux, dx, jdx, H.uc_lo[0], H.uc_lo[0] + H.uc_d[0], epsx, r, doubt);
-            if (deg_axis != 1) ok = ok && span_slab(uy, dy, jdy, H.uc_lo[1], H.uc_lo[1] + H.uc_d[1], epsx, r, doubt);
-            if (deg_axis != 2) ok = ok && span_slab(uz, dz, jdz, H.uc_lo[2], H.uc_lo[2] + H.uc_d[2], epsx, r, doubt);
-        }
         const SpanChild& K = ch[c];
-        if (ok) {
-            const double* p = K.p;
-            if (K.type == OP_CYL || K.type == OP_SPHERE) {
-                const double wx = ux - p[0], wy = uy - p[1], wz = uz - p[2];
-                double A = dx * dx + dy * dy + dz * dz, B = wx * dx + wy * dy + wz * dz, C = wx * wx + wy * wy + wz * wz;
-                if (K.type == OP_CYL) {
-                    const double dv = dx * p[3] + dy * p[4] + dz * p[5], wv = wx * p[3] + wy * p[4] + wz * p[5], ivv = p[6];
-                    A -= dv * dv * ivv;
-                    B -= wv * dv * ivv;
-                    C -= wv * wv * ivv;
-                    C -= p[7];
-                    // caps: 0 <= (w.v + t d.v) / v.v <= 1, inclusive (objects.go:339-341)
-                    const double cd = dv * ivv;
-                    ok = span_slab(wv * ivv, cd, 1.0 / cd, 0.0, 1.0, 1.0e-13, r, doubt);
-                } else {
-                    C -= p[3];
-                }
-                ok = ok && span_quadratic(fmax(A, 0.0), B, C, r, doubt);
-            } else if (K.type == OP_BOX) {
-                ok = ok && span_slab(ux, dx, jdx, p[0] - p[3], p[0] + p[3], epsx, r, doubt);
-                ok = ok && span_slab(uy, dy, jdy, p[1] - p[4], p[1] + p[4], epsx, r, doubt);
-                ok = ok && span_slab(uz, dz, jdz, p[2] - p[5], p[2] + p[5], epsx, r, doubt);
-            } else {  // parallelepiped: 0 < Minv (x - o) < 1 per component (objects.go:249-254)
-                const double wx = ux - p[0], wy = uy - p[1], wz = uz - p[2];
-#pragma unroll
-                for (int rr = 0; rr < 3; ++rr) {
-                    const double q0 = p[3 + 3 * rr] * wx + p[4 + 3 * rr] * wy + p[5 + 3 * rr] * wz;
-                    const double qd = p[3 + 3 * rr] * dx + p[4 + 3 * rr] * dy + p[5 + 3 * rr] * dz;
-                    ok = ok && span_slab(q0, qd, 1.0 / qd, 0.0, 1.0, epsx * (1.0 + p[12 + rr]), r, doubt);
-                }
-            }
+        SpanRange r;
+        if (!span_candidate_range(H, K, ray, R0, px, py, pz, deg_axis, r, doubt)) continue;
+        // End points -> lattice ordinals.  Common case: no lattice sample lies inside either doubt zone.  A candidate with one
+        // that does is set aside (fuzz list) and settled after this loop, sample by sample, with the reference's own expressions.
+        const double sc = P.s_center;
+        unsigned int near = 0u;
+        unsigned int e_in, e_out;
+        if (r.L1 <= r.U0) {  // some parameter is surely inside
+            e_in = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.L1) + sc, 0.5 * (r.L1 - r.L0), inv_ds, inv_dsf, near);
+            e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.U0 + r.U1) + sc, 0.5 * (r.U1 - r.U0), inv_ds, inv_dsf, near);
+        } else {
+            e_in = e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.U1) + sc, 0.5 * (r.U1 - r.L0), inv_ds, inv_dsf, near);
         }
-        if (!ok) continue;
-        if (r.L1 > r.U0) {  // no parameter is surely inside: any lattice sample between L0 and U1 is undecided
-            span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.U1) + P.s_center, 0.5 * (r.U1 - r.L0), inv_ds, inv_dsf, doubt);
+        if (near) {
+            if (!SETTLE || (flags & SPAN_HAS_WARP) || nfz >= kSpanFuzzCap) doubt |= 4u;  // (fast pass: flag it; a warp: cannot be settled here)
+            else fuzz[(nfz++) * kBlockThreads + tid] = code;
             continue;
         }
-        const unsigned int e_in = max(w_lo, span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.L1) + P.s_center, 0.5 * (r.L1 - r.L0), inv_ds, inv_dsf, doubt));
-        const unsigned int e_out = min(w_hi, span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.U0 + r.U1) + P.s_center, 0.5 * (r.U1 - r.U0), inv_ds, inv_dsf, doubt));
-        if (e_in >= e_out) continue;  // no lattice sample inside
+        e_in = max(max(w_lo, win_lo), e_in);
+        e_out = min(min(w_hi, win_hi), e_out);
+        if (e_in >= e_out) continue;  // no lattice sample inside (this window)
         if (niv < cap) {
             iv_in[niv * kBlockThreads + tid] = e_in | ((unsigned int)c << 26);
             iv_out[niv * kBlockThreads + tid] = e_out;
         } else {
-            overflow = true;
+            ovf = true;
         }
         ++niv;
     }
-    if (overflow) niv = 0;
+    if (SETTLE && __any_sync(FULL_MASK, nfz > 0)) {
+        for (int f = 0; f < nfz; ++f) {
+            const unsigned int code = fuzz[f * kBlockThreads + tid];
+            unsigned int e_in = 0u, e_out = 0u;
+            doubt |= span_settle<INTEG>(P, nfine, &H, ch, P.cams[view].eye, &ray, &R0, code, deg_axis, e_last, e_in, e_out);
+            if (deg_axis >= 0) {
+                const int pa = (int)((code >> (deg_axis == 0 ? 6 : (deg_axis == 1 ? 11 : 16))) & 31u) - 16;
+                const unsigned int w_lo = pa == dg.nA ? dg.eA : dg.e_sw, w_hi = (pa == dg.nA && dg.nA != dg.nB) ? dg.e_sw : dg.eB;
+                e_in = max(w_lo, e_in);
+                e_out = min(w_hi, e_out);
+            }
+            e_in = max(win_lo, e_in);
+            e_out = min(win_hi, e_out);
+            if (e_in >= e_out) continue;
+            if (niv < cap) {
+                iv_in[niv * kBlockThreads + tid] = e_in | ((code & 63u) << 26);
+                iv_out[niv * kBlockThreads + tid] = e_out;
+            } else {
+                ovf = true;
+            }
+            ++niv;
+        }
+    }
+    if (ovf) niv = 0;
 
     // ---- phase 3: integer sweep over the end points = the reference's loop, piece by piece ----
-    double T = 0.0;
-    unsigned int n_fine = 0;
-    if (niv > 0) {
+    if (!ovf && (niv > 0 || prev_z)) {
         const double dm = P.dm, DS = P.ds, dsf = P.ds_fine;
-        bool prev_z = false;  // prev_rho := 0.0 (main.go:179)
-        double facc = 0.0;    // sum of the fine samples seen so far in the coarse interval under way
-        // nothing before the first interval and nothing after the last one: both stretches add 0 and flip nothing
-        unsigned int e = e_last, e_stop = 0u;
+        // nothing before the first interval (unless the previous window ended inside material) and nothing after the last
+        // one: both stretches add 0 and flip nothing
+        unsigned int e = win_hi, e_stop = win_lo;
         for (int q = 0; q < niv; ++q) {
             e = min(e, iv_in[q * kBlockThreads + tid] & 0x3ffffffu);
             e_stop = max(e_stop, iv_out[q * kBlockThreads + tid]);
         }
-        e = max(e, e_first);
-        e_stop = min(e_stop + (INTEG == 1 ? 32u : 0u), e_last);  // (+2 coarse intervals: the exit transition's refinement)
+        e = prev_z ? win_lo : max(e, win_lo);
+        e_stop = min(max(e_stop, e) + (INTEG == 1 ? 32u : 0u), win_hi);  // (+2 coarse intervals: the exit transition's refinement)
         while (e < e_stop) {
             unsigned int next = e_stop;
             unsigned long long active = 0ull;
@@ -673,25 +864,41 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             e = next;
         }
     }
+    }  // windows
+    overflow = ovf;
+    if (!SETTLE) break;
+    if (!__any_sync(FULL_MASK, ovf && bl != nullptr && hit) || n_win >= 16u) break;
+    n_win *= 2u;   // (warp-uniform: every lane of the warp goes again, lanes that were fine just repeat their work)
+    redo = true;   // candidates straight from the bin: the candidate list shares its slots with the intervals and is gone
+    ncand = 0;
+    overflow = false;
+    }  // attempts
     if (overflow) doubt |= 32u;
     const bool bad = valid && doubt != 0u;
     const bool tile_bad = __any_sync(FULL_MASK, bad);
+    // fast pass: a warp tile whose only trouble is samples inside doubt zones goes to the settle pass, not to the marching kernels
+    // (samples inside doubt zones; more intervals than the list holds, when the tile has a bin to take the candidates from)
+    const bool settleable = (doubt & ~(4u | 32u)) == 0u && (!(doubt & 32u) || bl != nullptr);
+    const bool to_settle = !SETTLE && !(flags & SPAN_HAS_WARP) && tile_bad && !__any_sync(FULL_MASK, bad && !settleable);
     if ((tid & 31) == 0 && tile_bad) {
-        SA.tile_list[atomicAdd(SA.tile_count, 1u)] = item;
-        if (COUNT && P.stats) atomicAdd(P.stats + 6, 1ull);  // warp tiles handed to the marching kernels
+        if (to_settle) {
+            SA.settle_list[atomicAdd(SA.tile_count + 1, 1u)] = item;
+        } else {
+            SA.tile_list[atomicAdd(SA.tile_count, 1u)] = item;
+            if (COUNT && P.stats) atomicAdd(P.stats + 6, 1ull);  // warp tiles handed to the marching kernels
+        }
     }
-    if (COUNT && P.stats && bad) atomicOr(P.stats + 7, (unsigned long long)doubt);
+    if (COUNT && P.stats && bad && !to_settle) atomicOr(P.stats + 7, (unsigned long long)doubt);
 #ifdef XRAY_DEV_KNOBS
     if (P.dbg_cause == 77) {  // development builds: show which rays are handed over, and why
-        store_pixel(P, view, i, j, valid, bad ? -(double)doubt : exp(-(P.flat_field + T)));
-        XR_SPAN_NEXT;
+        store_pixel(P, view, i, j, valid, bad && !to_settle ? -(double)doubt : exp(-(P.flat_field + T)));
+        continue;
     }
 #endif
     store_pixel(P, view, i, j, valid, exp(-(P.flat_field + T)));
     if (COUNT && !tile_bad)
         add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, (unsigned long long)niv, 0ull, prim_tests, valid ? 1ull : 0ull);
-    }  // warp tiles of the chunk
-    }  // chunks
+    }  // warp tiles
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -781,11 +988,13 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
     const size_t tiles = (size_t)P.n_views * P.tiles_i * P.tiles_j;
     if (tiles == 0) return cudaSuccess;
     if (tiles * 4 > 0xffffffffull) return cudaErrorInvalidValue;
-    const size_t smem = span_kernel_smem_bytes(section_bytes);
+    const size_t smem_fast = span_smem_bytes(section_bytes, false), smem_settle = span_smem_bytes(section_bytes, true);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    SpanArgs SA = {d_section, section_bytes, d_tile_list, d_tile_count, (unsigned int)(tiles * 4), span_list_cap(section_bytes), nullptr, nullptr, 0u};
+    // work lists: d_tile_list[0 .. items) = hand-over to the marching kernels, [items .. 2 items) = settle pass
+    SpanArgs SA = {d_section, section_bytes, d_tile_list, d_tile_count, d_tile_list + tiles * 4, (unsigned int)(tiles * 4),
+                   span_list_cap(section_bytes, false), nullptr, nullptr, 0u};
     if (d_bins && bin_cap > 0 && n_instances > 0) {
         cudaError_t eb = cudaMemsetAsync(d_bins, 0, tiles * sizeof(unsigned int), stream);
         if (eb != cudaSuccess) return eb;
@@ -797,21 +1006,21 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
         SA.bin_lists = d_bins + tiles;
         SA.bin_cap = bin_cap;
     }
-    cudaError_t e0 = cudaMemsetAsync(d_tile_count, 0, 2 * sizeof(unsigned int), stream);  // hand-over count, work counter
+    cudaError_t e0 = cudaMemsetAsync(d_tile_count, 0, 2 * sizeof(unsigned int), stream);  // hand-over count, settle count
     if (e0 != cudaSuccess) return e0;
-#define XR_SGO(I, C)                                                                                       \
-    do {                                                                                                   \
-        auto kern = render_span_kernel<I, C>;                                                              \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                    \
-        /* persistent warps: exactly as many CTAs as are resident at once */                               \
-        int occ = 0;                                                                                       \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem);                \
-        if (e != cudaSuccess) return e;                                                                    \
-        const size_t resident = XR_SPAN_PERSISTENT ? (size_t)sms * (size_t)(occ > 0 ? occ : 1) : tiles;    \
-        const unsigned int grid = (unsigned int)(tiles < resident ? tiles : resident);                     \
-        kern<<<grid, kBlockThreads, smem, stream>>>(P, d_nfine, SA);                                       \
-        return cudaGetLastError();                                                                         \
+    SpanArgs SB = SA;
+    SB.cap = span_list_cap(section_bytes, true);
+    const unsigned int grid_settle = (unsigned int)(tiles < (size_t)sms ? tiles : (size_t)sms);
+#define XR_SGO(I, C)                                                                                                        \
+    do {                                                                                                                    \
+        auto fast = render_span_kernel<I, C, false>;                                                                        \
+        auto settle = render_span_kernel<I, C, true>;                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);            \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(settle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_settle); \
+        if (e != cudaSuccess) return e;                                                                                     \
+        fast<<<(unsigned int)tiles, kBlockThreads, smem_fast, stream>>>(P, d_nfine, SA);                                    \
+        settle<<<grid_settle, kBlockThreads, smem_settle, stream>>>(P, d_nfine, SB);                                        \
+        return cudaGetLastError();                                                                                          \
     } while (0)
     if (integrator == 0) {
         if (count) XR_SGO(0, true);

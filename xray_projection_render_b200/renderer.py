@@ -38,7 +38,8 @@ def _as_cam_array(cams):
 def _stats_dict(buf) -> dict:
     return {"ref_samples": int(buf[0]), "evaluated_samples": int(buf[1]), "fp64_fallbacks": int(buf[2]),
             "primitive_tests": int(buf[3]), "rays": int(buf[4]), "launches": int(buf[5]), "marched_tiles": int(buf[6]),
-            "march_reasons": int(buf[7])}
+            "march_reasons": int(buf[7]) & 0xFFFF, "span_renderer": bool(int(buf[7]) & 0x10000),
+            "clipping_smin": bool(int(buf[7]) & (1 << 17)), "clipping_smax": bool(int(buf[7]) & (1 << 18))}
 
 
 def render_scene(scene: Scene, cams, res: int, *, integration="hierarchical", precision="fp32", ds: float = -1.0,
