@@ -130,7 +130,11 @@ static void stage_release_locked() {
 // ~8-10 GB/s, the PCIe link delivers ~55, and a cgo / ctypes caller always hands over pageable memory.
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     int T = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / ((size_t)4 << 20)));
-    const unsigned hc = std::thread::hardware_concurrency();
+    unsigned hc = std::thread::hardware_concurrency();
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): the ranks share the host's cores
+        const int lw = atoi(e);
+        if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
+    }
     if (hc > 0) T = std::min<int>(T, std::max(1u, hc / 2));
     if (const char* e = getenv("XRAY_DRAIN_THREADS")) T = std::max(1, std::min(32, atoi(e)));
     if (T <= 1) {
