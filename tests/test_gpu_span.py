@@ -153,3 +153,85 @@ def test_clipping_flags_match_the_reference_probes(X, O, monkeypatch):
                     p = eye + d * s
                     got[e] = got[e] or osc.density(*p) > 0
         assert tuple(got) == want
+
+
+# ---- randomised scenes aimed at the interval renderer's special cases ---------------------------------------------------
+def _snap(rng, v, step=0.05):
+    """Coordinates on a coarse grid: faces, caps and centres then coincide with planes through the origin, with cell faces
+    and with each other -- the situations where a ray runs inside a bounding plane or meets a surface exactly on a lattice sample."""
+    return float(np.round(v / step) * step) if rng.random() < 0.6 else float(v)
+
+
+def _convex_prim(rng, lo, hi, snap=True):
+    ext = hi - lo
+    c = lo + rng.uniform(0.15, 0.85, 3) * ext
+    s = float(ext.min())
+    f = (lambda v: _snap(rng, v)) if snap else float
+    t = rng.choice(["sphere", "box", "cube", "cylinder", "parallelepiped"])
+    rho = float(rng.choice([1.0, 0.7, 0.35, -0.5, -1.0, 0.15]))
+    if t == "sphere":
+        return {"type": t, "center": [f(v) for v in c], "radius": float(rng.uniform(0.1, 0.45) * s), "rho": rho}
+    if t == "box":
+        return {"type": t, "center": [f(v) for v in c], "sides": [f(v) + 0.05 for v in rng.uniform(0.1, 0.7, 3) * ext], "rho": rho}
+    if t == "cube":
+        return {"type": t, "center": [f(v) for v in c], "side": f(rng.uniform(0.15, 0.6) * s) + 0.05, "rho": rho}
+    if t == "cylinder":
+        axis = rng.integers(0, 4)
+        d = rng.uniform(-0.45, 0.45, 3) * ext
+        if axis < 3:  # axis-parallel struts: caps parallel to cell faces and image rows / columns
+            d = np.zeros(3)
+            d[axis] = rng.uniform(0.2, 0.6) * ext[axis] * rng.choice([-1, 1])
+        p0 = np.array([f(v) for v in c])
+        return {"type": t, "p0": list(p0), "p1": [f(v) for v in p0 + d + 1e-3], "radius": float(rng.uniform(0.04, 0.2) * s), "rho": rho}
+    m = np.eye(3) * rng.uniform(0.2, 0.6, 3) * ext + rng.uniform(-0.1, 0.1, (3, 3)) * s
+    return {"type": t, "origin": [f(v) for v in c - 0.3 * ext], "v0": list(m[0]), "v1": list(m[1]), "v2": list(m[2]), "rho": rho}
+
+
+def _span_scene(rng):
+    kind = rng.choice(["flat", "tess", "tess", "bare"])
+    if kind == "bare":
+        return _convex_prim(rng, np.array([-0.6] * 3), np.array([0.6] * 3))
+    if kind == "flat":
+        n = int(rng.integers(2, 12))
+        return {"type": "object_collection", "greedy_dens_eval": bool(rng.random() < 0.4),
+                "objects": [_convex_prim(rng, np.array([-0.7] * 3), np.array([0.7] * 3)) for _ in range(n)]}
+    cell = np.array([rng.choice([0.25, 0.3, 0.4, 0.5, 0.8]) for _ in range(3)])
+    lo = np.array([rng.choice([0.0, -0.1, -cell[a] / 2, 0.05]) for a in range(3)])
+    objs = []
+    for _ in range(int(rng.integers(1, 7))):
+        p = _convex_prim(rng, lo, lo + cell)
+        if rng.random() < 0.8:
+            p["rho"] = abs(p["rho"])
+        objs.append(p)
+    uc = {"objects": {"objects": objs}, "xmin": lo[0], "xmax": lo[0] + cell[0], "ymin": lo[1], "ymax": lo[1] + cell[1],
+          "zmin": lo[2], "zmax": lo[2] + cell[2]}
+    b = [rng.choice([0.6, 0.75, 0.8, 0.9]) for _ in range(3)]
+    return {"type": "tessellated_obj_coll", "uc": uc, "xmin": -b[0], "xmax": b[0], "ymin": -b[1], "ymax": b[1], "zmin": -b[2], "zmax": b[2]}
+
+
+def _span_warp(rng):
+    t = rng.choice(["none", "none", "none", "rigid", "linear", "affine"])
+    if t == "none":
+        return None
+    if t == "rigid":
+        return {"type": t, "displacements": [_snap(rng, v) for v in rng.uniform(-0.2, 0.2, 3)]}
+    if t == "linear":
+        return {"type": t, "strains": list(rng.uniform(-0.1, 0.1, 6))}
+    return {"type": t, "matrix": (np.eye(3) + rng.uniform(-0.15, 0.15, (3, 3))).tolist()}
+
+
+@pytest.mark.parametrize("seed", range(300))
+def test_random_convex_scene_special_views(X, O, seed):
+    """Axis-aligned and diagonal views at polar = 90 (rays inside cell-face / cap / box-face planes, surfaces met exactly on
+    lattice samples, rays through cell edges), snapped geometry, both integrators, odd detector sizes, both precisions."""
+    rng = np.random.default_rng(9000 + seed)
+    obj = _span_scene(rng)
+    deform = _span_warp(rng)
+    integ = "hierarchical" if rng.random() < 0.7 else "simple"
+    res = int(rng.choice([17, 32, 33, 48]))
+    ds = float(rng.choice([0.03, 0.02, 0.0125, 0.01, 0.005]))
+    az = float(rng.choice([0.0, 90.0, 180.0, 270.0, 45.0, 135.0, 30.0, rng.uniform(0, 360)]))
+    pol = float(rng.choice([90.0, 90.0, 90.0, 60.0, rng.uniform(40, 140)]))
+    out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=((az, pol),), res=res, integ=integ, ds=ds, ff=float(rng.choice([0.0, 0.1])),
+                                 dm=float(rng.choice([1.0, 0.5, 2.0])))
+    assert_parity(out, nref)  # (a scene without any positive density is not eligible and takes the marching kernels: fine)
