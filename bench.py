@@ -350,7 +350,6 @@ def measure(X, torch, dist, name, rank, world, local_rank, steps, warmup, flush,
             e2e_api = "XRayRenderVolumeExCUDA"
         else:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            host_t = {}
 
             def step_e2e(host_out):
                 # rank 0 uploads the volume ONCE, one NCCL broadcast over NVLink replicates it, every rank renders its views
@@ -360,16 +359,12 @@ def measure(X, torch, dist, name, rank, world, local_rank, steps, warmup, flush,
                 ev0.record(stream)
                 dist.broadcast(vol_dev, src=0)
                 ev1.record(stream)
-                if n:
-                    X.render_volume_device(vol_dev, (nvox, nvox, nvox), cams, res, out_dev, ds=ds_v, stream=stream.cuda_stream)
-                    key = host_out.ctypes.data
-                    if key not in host_t:
-                        host_t[key] = torch.from_numpy(host_out)
-                    host_t[key].copy_(out_dev[:n], non_blocking=False)
-                torch.cuda.synchronize()
+                stream.synchronize()   # the library renders on its own stream: the broadcast has to be complete
+                if n:  # kernels, image D2H and the copy into the caller's buffer overlapped inside the library
+                    X.render_volume_device_to_host(vol_dev, (nvox, nvox, nvox), cams, res, host_out, ds=ds_v)
                 bcast_ms.append(ev0.elapsed_time(ev1))
             h2d_step = vol_dev.numel() * 4 if rank == 0 else 0
-            e2e_api = "pinned H2D on rank 0 + ncclBroadcast + XRayRenderVolumeDeviceCUDA + D2H"
+            e2e_api = "pinned H2D on rank 0 + ncclBroadcast + XRayRenderVolumeDeviceToHostCUDA"
     else:
         scene = X.Scene(str(SCENES / obj), str(SCENES / deform) if deform else None)
         ds_v = scene.auto_ds() if ds <= 0 else ds
@@ -575,7 +570,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     line = {
         "metric": "Gsamples/s", "value": main["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32" if is_volume else "f64 intervals / f32 images", "data": "synthetic",
+        "dtype": "f32" if is_volume else ("f64" if main["roofline"].get("flops_model", {}).get("kernel") == "render_span_kernel" else "f32"),
+        "data": "synthetic",
         "projections_512_per_s": main["projections_512_per_s"], "rays_per_s": main["rays_per_s"],
         "config": {"workload": main["workload"], "views_total": main["views_rendered"],
                    "sharding": "views modulo rank (main.go:244 --jobs_modulo/--job); fixed view list, so N ranks share the same work",

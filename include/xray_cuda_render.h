@@ -169,6 +169,12 @@ int XRayRenderVolumeExCUDA(const void* volume, int volume_dtype, int nx, int ny,
 int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
                                int num_cameras, int image_res, const XRayRenderOpts* opts, void* d_out_images);
 
+/* Device-resident volume, HOST images (synchronous): what a process uses whose copy of the volume arrived over NVLink
+ * (one rank uploads, ncclBroadcast replicates) but whose images go back to the host -- kernels, the D2H of each batch
+ * and the copy into the caller's (pageable or pinned) buffer are overlapped like in XRayRenderVolumeExCUDA. */
+int XRayRenderVolumeDeviceToHostCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
+                                     int num_cameras, int image_res, const XRayRenderOpts* opts, void* out_images);
+
 /* Voxelise a compiled scene (density() semantics of main.go computeVoxel:208-214):
  * out_volume[k*res*res + i*res + j] = density(i/res*2-1, j/res*2-1, k/res*2-1), fp32, host buffer. */
 int XRayVoxelizeSceneCUDA(XRayScene* scene, int res, double density_multiplier, float* out_volume);

@@ -17,7 +17,7 @@ def _check(X, O, obj, deform=None, *, views, res, ds=-1.0, integs=("hierarchical
         assert_parity(out, nref)
         for prec in ("fp32", "fp64"):
             st = out[prec][1]
-            assert st["launches"] == 2, "interval renderer + tile-list pass expected"
+            assert st["span_renderer"] and st["launches"] >= 3, "interval renderer (fast pass, settle pass) + hand-over pass expected"
             if max_marched is not None:
                 assert st["marched_tiles"] <= max_marched, st
             worst = max(worst, out[prec][0])
@@ -31,7 +31,7 @@ def test_span_is_the_default_path_for_convex_scenes(X, O, scenes):
     sc = X.Scene(str(scenes / "lattice.json"), str(scenes / "deformation_sigmoid.json"))
     cams = X.cameras_from_angles([(77.0, 83.0)], R, FOV)
     _, st = X.render_scene(sc, cams, 24, return_stats=True)
-    assert st["launches"] == 1 and st["marched_tiles"] == 0
+    assert not st["span_renderer"] and st["marched_tiles"] == 0
 
 
 @pytest.mark.parametrize("warp", [
@@ -115,7 +115,7 @@ def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkey
         monkeypatch.delenv("XRAY_NO_SPAN")
         assert np.abs(a.astype(np.float64) - b).max() <= 2e-6
         assert sa["ref_samples"] == sb["ref_samples"]
-        assert sa["launches"] == 2 and sb["launches"] == 1
+        assert sa["span_renderer"] and not sb["span_renderer"] and sa["launches"] > sb["launches"]
         assert sa["marched_tiles"] <= 0.002 * 2 * (res // 4) * (res // 8), sa  # warp tiles of 4 x 8 pixels
 
 

@@ -119,6 +119,29 @@ def test_device_resident_volume(X, O):
     assert np.abs(host.astype(np.float64) - ref).max() <= TOL_FP32
 
 
+def test_device_volume_to_host_images(X, O):
+    """XRayRenderVolumeDeviceToHostCUDA: device-resident volume (as after an NCCL broadcast), images into pageable and pinned
+    host buffers; bit-identical to the host-volume entry point."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    vol = rng.random((24, 20, 28), dtype=np.float32)   # nx=20, ny=28, nz=24
+    views = [(30.0, 90.0), (120.0, 80.0), (250.0, 100.0), (77.0, 90.0)]
+    cams = X.cameras_from_angles(views, R, FOV)
+    ds = 2.0 / 20 / 5.0
+    dvol = torch.from_numpy(vol).cuda()
+    torch.cuda.synchronize()
+    want = X.render_volume(vol, cams, 33, ds=ds)
+    out = np.zeros((4, 33, 33), dtype=np.float32)
+    X.render_volume_device_to_host(dvol, (20, 28, 24), cams, 33, out, ds=ds)
+    assert np.array_equal(out, want)
+    pin = torch.zeros((4, 33, 33), dtype=torch.float32, pin_memory=True)
+    X.render_volume_device_to_host(dvol, (20, 28, 24), cams, 33, pin.numpy(), ds=ds)
+    assert np.array_equal(pin.numpy(), want)
+    osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)})
+    ref = np.stack([osc.render_view(*O.camera_from_angles(az, pol, R), 33, FOV, R, ds, "simple")[0] for az, pol in views])
+    assert np.abs(out.astype(np.float64) - ref).max() <= TOL_FP32
+
+
 # ---- legacy voxeliser symbols -----------------------------------------------------------
 def ref_voxelize(cyls, res, dm):
     """fp32 restatement of the reference kernel (cuda_backend.cu:208-252): segment distance test,

@@ -26,7 +26,8 @@ EXTENDED_SYMBOLS = (
     "XRayLastError", "XRayDeviceCount", "XRayReleaseCaches", "XRayRenderOptsInit", "XRaySceneCompileJSON", "XRaySceneFree",
     "XRaySceneMinFeatureSize", "XRaySceneProgram", "XRaySceneBounds", "XRaySceneNumVoxelSlots", "XRaySceneVoxelDims",
     "XRaySceneSetVoxelData", "XRaySceneDensityHost", "XRayCameraFromAngles", "XRayRenderSceneCUDA",
-    "XRayRenderSceneDeviceCUDA", "XRayRenderVolumeExCUDA", "XRayRenderVolumeDeviceCUDA", "XRayVoxelizeSceneCUDA",
+    "XRayRenderSceneDeviceCUDA", "XRayRenderVolumeExCUDA", "XRayRenderVolumeDeviceCUDA", "XRayRenderVolumeDeviceToHostCUDA",
+    "XRayVoxelizeSceneCUDA",
     "XRayMeasureFp32Peak",
 )
 
@@ -142,6 +143,8 @@ def load() -> ctypes.CDLL:
     L.XRayRenderVolumeExCUDA.argtypes = [c_void_p, c_int, c_int, c_int, c_int, cam64p, c_int, c_int, optp, c_void_p]
     L.XRayRenderVolumeDeviceCUDA.restype = c_int
     L.XRayRenderVolumeDeviceCUDA.argtypes = [c_void_p, c_int, c_int, c_int, cam64p, c_int, c_int, optp, c_void_p]
+    L.XRayRenderVolumeDeviceToHostCUDA.restype = c_int
+    L.XRayRenderVolumeDeviceToHostCUDA.argtypes = [c_void_p, c_int, c_int, c_int, cam64p, c_int, c_int, optp, c_void_p]
     L.XRayVoxelizeSceneCUDA.restype = c_int
     L.XRayVoxelizeSceneCUDA.argtypes = [c_void_p, c_int, c_double, fp]
     L.XRayMeasureFp32Peak.restype = c_int

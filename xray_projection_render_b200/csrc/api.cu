@@ -839,8 +839,8 @@ static int run_job(Job& J) {
     };
     // parity: which tile list / event to use; march_stream: where the hand-over pass goes (the job's stream, or the auxiliary
     // one, so that it overlaps the next batch's span kernel -- a handful of hard warp tiles take ~1 ms on their own)
+    // (n_launches counts the kernels of this library that are launched: stats[5], bench.py's gpu_launches)
     auto launch = [&](int v0, int n, void* d_dst, int parity, cudaStream_t march_stream) -> cudaError_t {
-        ++n_launches;
         P.cams = C->d_cams + v0;
         P.n_views = n;
         P.out = d_dst;
@@ -857,19 +857,24 @@ static int run_job(Job& J) {
                 P.smem_prog_bytes = 0;
             }
             cudaError_t ec = launch_clip_probe(P, stream);
+            ++n_launches;
             P.prog_in_smem = smem_flag;
             P.smem_prog_bytes = smem_bytes;
             if (ec != cudaSuccess) return ec;
         }
-        if (!use_span) return launch_march(stream);
+        if (!use_span) {
+            ++n_launches;
+            return launch_march(stream);
+        }
         unsigned int* tl = C->d_tile_list[parity];
         cudaError_t es = launch_render_span(P, J.opts.integration, P.stats != nullptr, C->d_nfine, ds->d_blob + h->span_off, h->span_bytes,
                                             tl + 2, tl, bin_cap ? C->d_bins : nullptr, bin_cap, n_instances, stream);
         if (es != cudaSuccess) return es;
+        n_launches += bin_cap ? 3 : 2;  // (binning,) fast pass, settle pass
 #ifdef XRAY_DEV_KNOBS
         if (P.dbg_cause == 77) return es;  // leave the interval renderer's hand-over codes in the image
 #endif
-        ++n_launches;
+        ++n_launches;  // the marching kernels' pass over the hand-over list
         if (march_stream != stream) {
             es = cudaEventRecord(C->ev_span[parity], stream);
             if (es == cudaSuccess) es = cudaStreamWaitEvent(march_stream, C->ev_span[parity], 0);
@@ -1378,6 +1383,27 @@ int XRayRenderVolumeDeviceCUDA(const float* d_volume, int nx, int ny, int nz, co
     else XRayRenderOptsInit(&o);
     int rc = render_common(sc, cameras, num_cameras, image_res, opts, d_out_images, true, d_volume,
                            volume_fast_path_ok(o, XRAY_VOXEL_F32));
+    std::string keep = g_last_error;
+    XRaySceneFree(sc);
+    g_last_error = keep;
+    return rc;
+} catch (const std::bad_alloc&) {
+    return fail(9, "out of host memory");
+} catch (...) {
+    return fail(9, "internal error");
+}
+
+int XRayRenderVolumeDeviceToHostCUDA(const float* d_volume, int nx, int ny, int nz, const XRayCameraParams64* cameras,
+                                     int num_cameras, int image_res, const XRayRenderOpts* opts, void* out_images) try {
+    if (!d_volume || !cameras || !out_images) return fail(1, "null pointer argument");
+    if (nx <= 0 || ny <= 0 || nz <= 0 || image_res <= 0 || num_cameras <= 0) return fail(2, "dimensions must be positive");
+    XRayScene* sc = nullptr;
+    if (int rc = make_volume_scene(nx, ny, nz, &sc)) return rc;
+    XRayRenderOpts o;
+    if (opts) o = *opts;
+    else XRayRenderOptsInit(&o);
+    o.num_devices = 0;  // the volume lives on the current device
+    int rc = render_common(sc, cameras, num_cameras, image_res, &o, out_images, false, d_volume, volume_fast_path_ok(o, XRAY_VOXEL_F32));
     std::string keep = g_last_error;
     XRaySceneFree(sc);
     g_last_error = keep;

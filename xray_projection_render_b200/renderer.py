@@ -135,6 +135,22 @@ def render_volume_device(d_volume, dims, cams, res: int, out, *, ds: float, inte
     return out
 
 
+def render_volume_device_to_host(d_volume, dims, cams, res: int, out: np.ndarray, *, ds: float, integration="simple",
+                                 precision="fp32", flat_field: float = 0.0, density_multiplier: float = 1.0, return_stats: bool = False):
+    """Device-resident fp32 volume (torch CUDA tensor [z][x][y] or int pointer), images into the HOST array ``out``
+    (float32 / float64, pageable or pinned); synchronous.  The caller orders the volume's producer before the call."""
+    L = _lib.load()
+    cams = _as_cam_array(cams)
+    nx, ny, nz = dims
+    vptr = d_volume.data_ptr() if hasattr(d_volume, "data_ptr") else int(d_volume)
+    stats = (ctypes.c_uint64 * _lib.XRAY_NUM_STATS)()
+    o = _lib.make_opts(integration, precision, "f64" if out.dtype == np.float64 else "f32", ds, flat_field, density_multiplier, None, 0,
+                       stats if return_stats else None)
+    _lib.check(L.XRayRenderVolumeDeviceToHostCUDA(ctypes.c_void_p(vptr), nx, ny, nz, cams, len(cams), res, ctypes.byref(o),
+                                                  out.ctypes.data_as(ctypes.c_void_p)))
+    return (out, _stats_dict(stats)) if return_stats else out
+
+
 def voxelize_scene(scene: Scene, res: int, density_multiplier: float = 1.0) -> np.ndarray:
     """density() on the export grid of main.go:208-214 -> float32 [k][i][j]."""
     out = np.empty((res, res, res), dtype=np.float32)
