@@ -19,7 +19,7 @@ def _check(X, O, obj, deform=None, *, views, res, ds=-1.0, integs=("hierarchical
             st = out[prec][1]
             assert st["span_renderer"] and st["launches"] >= 3, "interval renderer (fast pass, settle pass) + hand-over pass expected"
             if max_marched is not None:
-                assert st["marched_tiles"] <= max_marched, st
+                assert st["marched_tiles"] <= max_marched, (st["marched_tiles"], hex(st["march_reasons"]), integ, prec)
             worst = max(worst, out[prec][0])
     return worst
 
@@ -101,6 +101,57 @@ def test_fine_lattice_and_window_edges(X, O):
                                                     {"type": "sphere", "center": [0.0, 1.8, 0.0], "radius": 0.4, "rho": 0.5},
                                                     {"type": "box", "center": [0.0, 0.0, -0.3], "sides": [4.0, 0.2, 0.1], "rho": -0.1}]}
     _check(X, O, obj, views=((0.0, 90.0), (90.0, 85.0), (33.0, 90.0)), res=24, ds=0.0004, max_marched=12)
+
+
+def test_rays_inside_bounding_planes_are_settled_not_marched(X, O, scenes):
+    """Axis-aligned views, even image sizes (pixel res / 2 sits at 0 exactly, main.go:463): the central row and column run INSIDE
+    the planes z = 0 / y = 0, which hold a face of each box and a cap of each cylinder here -- like the cap planes of BASELINE
+    config 1's hole at azimuth 0 / 90 / ....  The settle pass decides such a constraint sample by sample with the reference's
+    expressions (span_settle: one monotone step per plane, bisected) instead of handing the tiles to the marching kernels.
+    Only the central pixel, where the planes of all four primitives meet, may still go there."""
+    obj = {"type": "object_collection", "objects": [
+        {"type": "box", "center": [0.0, 0.0, 0.25], "sides": [0.9, 0.7, 0.5], "rho": 0.6},             # face z = 0: the central row at polar 90
+        {"type": "cylinder", "p0": [0.1, 0.0, -0.4], "p1": [0.1, 0.0, 0.0], "radius": 0.25, "rho": -0.3},  # cap in z = 0, axis along z
+        {"type": "cylinder", "p0": [0.0, 0.0, 0.1], "p1": [0.0, 0.6, 0.1], "radius": 0.07, "rho": 0.2},   # cap in y = 0: central column at az 0 / 180
+        {"type": "box", "center": [-0.3, 0.2, -0.2], "sides": [0.2, 0.4, 0.1], "rho": 0.3}]}            # face y = 0
+    views = ((0.0, 90.0), (90.0, 90.0), (180.0, 90.0), (270.0, 90.0), (0.0, 0.0001), (45.0, 90.0))
+    _check(X, O, obj, views=views, res=33, ds=0.0137, max_marched=0)
+    _check(X, O, obj, views=views, res=64, ds=0.0137, max_marched=4)
+    _check(X, O, str(scenes / "cube_w_hole.json"), views=((0.0, 90.0), (90.0, 90.0), (180.0, 90.0), (270.0, 90.0)), res=65, max_marched=0)
+    _check(X, O, str(scenes / "cube_w_hole.json"), views=((0.0, 90.0), (90.0, 90.0)), res=128, max_marched=1)
+
+
+def test_rays_along_edges_and_non_monotone_planes_are_handed_over(X, O):
+    """Two undecided planes at once (the central ray runs along an edge of a box: the members can sit in the middle of the
+    range) and a plane constraint whose rounded expression need not be monotone along the ray (a cap of a diagonal cylinder,
+    a face of a sheared parallelepiped, both containing the eye): neither is bisected; the image must match all the same."""
+    s2 = 0.5 ** 0.5
+    obj = {"type": "object_collection", "objects": [
+        {"type": "box", "center": [0.0, 0.2, 0.15], "sides": [0.8, 0.4, 0.3], "rho": 0.5},                # edge y = 0, z = 0 along x
+        {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.3 * s2, 0.0, 0.3 * s2], "radius": 0.2, "rho": 0.3},  # cap plane x + z = 0
+        {"type": "parallelepiped", "origin": [0.0, 0.0, 0.0], "v0": [0.3, 0.0, -0.3], "v1": [0.0, -0.4, 0.0], "v2": [0.2, 0.0, 0.25],
+         "rho": 0.4}]}
+    views = ((0.0, 90.0), (180.0, 90.0), (90.0, 45.0), (270.0, 135.0), (90.0, 135.0))
+    for res in (33, 48):
+        _check(X, O, obj, views=views, res=res, ds=0.0093)
+    _, st = X.render_scene(X.Scene(obj), X.cameras_from_angles([(0.0, 90.0)], R, FOV), 48, ds=0.0093, return_stats=True)
+    assert st["marched_tiles"] >= 1 and st["march_reasons"] & 2
+
+
+def test_rays_along_cell_edges_of_a_tessellation(X, O, scenes):
+    """Even image sizes put the central ray on a cell EDGE of the lattice at axis-aligned views (two coordinates inside face
+    planes at once); the settle pass bisects each axis' period step on its own."""
+    uc = {"objects": {"objects": [{"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.12, "rho": 0.9},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.3, 0.0, 0.0], "radius": 0.04, "rho": 0.5},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.0, 0.3, 0.0], "radius": 0.05, "rho": 0.4},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.0, 0.0, 0.3], "radius": 0.03, "rho": 0.3},
+                                  {"type": "box", "center": [0.15, 0.0, 0.3], "sides": [0.1, 0.1, 0.1], "rho": 0.7}]},
+          "xmin": 0.0, "xmax": 0.3, "ymin": 0.0, "ymax": 0.3, "zmin": 0.0, "zmax": 0.3}
+    obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.75, "xmax": 0.75, "ymin": -0.6, "ymax": 0.6, "zmin": -0.45, "zmax": 0.9}
+    views = ((0.0, 90.0), (90.0, 90.0), (180.0, 90.0), (270.0, 90.0), (0.0, 0.0001), (0.0, 179.9999))
+    _check(X, O, obj, views=views, res=32, ds=0.011, max_marched=16)
+    _check(X, O, obj, views=views, res=33, ds=0.011, max_marched=0)
+    _check(X, O, str(scenes / "lattice.json"), views=((0.0, 90.0), (90.0, 90.0)), res=64, max_marched=2)
 
 
 def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkeypatch):

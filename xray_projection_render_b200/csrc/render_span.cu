@@ -18,6 +18,7 @@
 // `doubt` for the ray.  Tiles with a doubtful ray (and rays that overflow the small per-ray lists) are flagged and
 // re-rendered by the marching kernels, which settle such samples with the reference's own operation order.  The
 // result therefore equals the marching kernels' to ~1e-15 in T, in both precision modes.
+#include <cstdio>
 #include "eval.cuh"
 
 namespace xr {
@@ -73,11 +74,15 @@ struct SpanRange {
 
 // lo <= c0 + cd * t <= hi.  A coordinate that does not move over the window (|cd| < 1e-9, |t| <= 1.75) is decided from
 // c0 alone, with doubt when it sits within 4e-9 of a bound (a ray running inside a face plane).  eps bounds the
-// rounding error of the coordinate as the reference computes it.
+// rounding error of the coordinate as the reference computes it.  Doubt bits: see render_span_kernel.
 __device__ __forceinline__ bool span_slab(double c0, double cd, double inv_cd, double lo, double hi, double eps, SpanRange& r, unsigned int& doubt) {
     if (fabs(cd) < 1.0e-9) {
         const double dl = c0 - lo, dh = hi - c0;
-        if (fabs(dl) < 4.0e-9 + eps || fabs(dh) < 4.0e-9 + eps) doubt |= 1u;  // a ray inside a bounding plane
+        const bool nl = fabs(dl) < 4.0e-9 + eps, nh = fabs(dh) < 4.0e-9 + eps;
+        if (nl || nh) {  // a ray inside a bounding plane: undecided here, so the constraint passes and the settle pass (or the
+            doubt = (doubt | (nl && nh ? 3u : 1u)) + 0x100u;  // marching kernels) decide sample by sample.  Bits 8.. count these
+            return true;                                      // constraints (span_settle needs to know whether there is just one)
+        }
         return dl >= 0.0 && dh >= 0.0;
     }
     double a = (lo - c0) * inv_cd, b = (hi - c0) * inv_cd;
@@ -112,24 +117,29 @@ __device__ __forceinline__ bool span_quadratic(double A, double B, double C, Spa
     return r.L0 <= r.U1;
 }
 
+// A sum of products whose terms move in opposite directions along the ray need not be monotone once rounded: such a
+// constraint cannot be bisected (span_settle) when the ray runs inside its plane.
+__device__ __forceinline__ bool span_mixed(double a, double b, double c) { return (a > 0.0 || b > 0.0 || c > 0.0) && (a < 0.0 || b < 0.0 || c < 0.0); }
+
 // The ray in object space, centred on the window (x(t) = c + d t, t = s - R), with what the slabs need.
 struct SpanRay {
     double cx, cy, cz, dx, dy, dz, jdx, jdy, jdz, epsx;
 };
 
 // Parameter range of the ray inside child K of period (px, py, pz), intersected with R0 (the outer box): three period
-// slabs (not along a degenerate axis, whose period is settled per ordinal), then the primitive.
+// slabs (not along the axes of skip_axes, bit a = axis a: a degenerate axis, whose period is settled per ordinal), then the primitive.
+template <bool MIXED>  // MIXED: also flag the plane constraints that span_settle must not bisect (span_mixed); the fast pass does not care
 __device__ __forceinline__ bool span_candidate_range(const SpanHeader& H, const SpanChild& K, const SpanRay& y, const SpanRange& R0, int px, int py,
-                                                     int pz, int deg_axis, SpanRange& r, unsigned int& doubt) {
+                                                     int pz, int skip_axes, SpanRange& r, unsigned int& doubt) {
     const double dx = y.dx, dy = y.dy, dz = y.dz, epsx = y.epsx;
     // ray centre in the coordinates of this period: x' = x - dx * n (objects.go:571)
     const double ux = y.cx - H.uc_d[0] * (double)px, uy = y.cy - H.uc_d[1] * (double)py, uz = y.cz - H.uc_d[2] * (double)pz;
     r = R0;
     bool ok = true;
     if (H.flags & SPAN_TESS) {  // the period's own cell: floor((x - min) / d) == n  <=>  min <= x' < min + d
-        if (deg_axis != 0) ok = ok && span_slab(ux, dx, y.jdx, H.uc_lo[0], H.uc_lo[0] + H.uc_d[0], epsx, r, doubt);
-        if (deg_axis != 1) ok = ok && span_slab(uy, dy, y.jdy, H.uc_lo[1], H.uc_lo[1] + H.uc_d[1], epsx, r, doubt);
-        if (deg_axis != 2) ok = ok && span_slab(uz, dz, y.jdz, H.uc_lo[2], H.uc_lo[2] + H.uc_d[2], epsx, r, doubt);
+        if (!(skip_axes & 1)) ok = ok && span_slab(ux, dx, y.jdx, H.uc_lo[0], H.uc_lo[0] + H.uc_d[0], epsx, r, doubt);
+        if (!(skip_axes & 2)) ok = ok && span_slab(uy, dy, y.jdy, H.uc_lo[1], H.uc_lo[1] + H.uc_d[1], epsx, r, doubt);
+        if (!(skip_axes & 4)) ok = ok && span_slab(uz, dz, y.jdz, H.uc_lo[2], H.uc_lo[2] + H.uc_d[2], epsx, r, doubt);
     }
     if (!ok) return false;
     const double* p = K.p;
@@ -144,7 +154,9 @@ __device__ __forceinline__ bool span_candidate_range(const SpanHeader& H, const 
             C -= p[7];
             // caps: 0 <= (w.v + t d.v) / v.v <= 1, inclusive (objects.go:339-341)
             const double cd = dv * ivv;
+            const unsigned int d0 = doubt;
             ok = span_slab(wv * ivv, cd, 1.0 / cd, 0.0, 1.0, 1.0e-13, r, doubt);
+            if (MIXED && doubt != d0 && span_mixed(dx * p[3], dy * p[4], dz * p[5])) doubt |= 2u;
         } else {
             C -= p[3];
         }
@@ -159,7 +171,9 @@ __device__ __forceinline__ bool span_candidate_range(const SpanHeader& H, const 
         for (int rr = 0; rr < 3; ++rr) {
             const double q0 = p[3 + 3 * rr] * wx + p[4 + 3 * rr] * wy + p[5 + 3 * rr] * wz;
             const double qd = p[3 + 3 * rr] * dx + p[4 + 3 * rr] * dy + p[5 + 3 * rr] * dz;
+            const unsigned int d0 = doubt;
             ok = ok && span_slab(q0, qd, 1.0 / qd, 0.0, 1.0, epsx * (1.0 + p[12 + rr]), r, doubt);
+            if (MIXED && doubt != d0 && span_mixed(dx * p[3 + 3 * rr], dy * p[4 + 3 * rr], dz * p[5 + 3 * rr])) doubt |= 2u;
         }
     }
     return ok;
@@ -233,6 +247,17 @@ __device__ __forceinline__ unsigned int span_next_ordinal(const unsigned char* _
     return j < (unsigned int)__ldg(nfine + k) ? e + 1u : 16u * k + 15u;
 }
 
+template <int INTEG>
+__device__ __forceinline__ unsigned int span_prev_ordinal(const unsigned char* __restrict__ nfine, unsigned int e) {
+    if (INTEG == 0) return e - 1u;
+    const unsigned int k = e >> 4, j = e & 15u;
+    if (j == 15u) {
+        const unsigned int nf = (unsigned int)__ldg(nfine + k);
+        return nf > 0u ? 16u * k + nf : 16u * (k - 1u) + 15u;
+    }
+    return j <= 1u ? 16u * (k - 1u) + 15u : e - 1u;
+}
+
 // Does the reference see lattice sample e of this ray inside child K of period (px, py, pz)?  The reference's own
 // expressions in its own operation order (no FMA): position main.go:147-149, outer bounds / fold / unit-cell bounds
 // objects.go:568-582, 458-464, primitive tests objects.go:63-72, 171-179, 247-255, 334-350.  Cold: only lattice samples
@@ -278,11 +303,14 @@ __device__ __forceinline__ bool span_exact_member(const RenderParams& P, const u
 // Settle the lattice samples that lie inside the doubt zone of an interval's end point(s) one by one with the reference's own
 // expressions: by convexity the first member from the lower side and the first non-member after it fix [e_in, e_out).
 // Cold and out of line (called after the hot loop for the few candidates it set aside): recomputes the candidate's range.
-// Returns doubt bits (0 = settled; e_in >= e_out = no lattice sample inside).
+// [e_first, e_last) = the ordinals to look at: the lattice window, cut to where the ray folds into this candidate's period
+// along degenerate axes.  Returns doubt bits (0 = settled; e_in >= e_out = no lattice sample inside).
 template <int INTEG>
 __device__ __noinline__ unsigned int span_settle(const RenderParams& P, const unsigned char* __restrict__ nfine, const SpanHeader* H,
                                                  const SpanChild* ch, const double* __restrict__ eye, const SpanRay* ray, const SpanRange* R0,
-                                                 unsigned int code, int deg_axis, unsigned int e_last, unsigned int& e_in, unsigned int& e_out) {
+                                                 unsigned int code, int skip_axes, unsigned int e_first, unsigned int e_last, unsigned int& e_in,
+                                                 unsigned int& e_out) {
+    const bool fuzzy = (code >> 31) != 0u;  // some constraint of this candidate is a ray inside its bounding plane (span_slab)
     const int c = (int)(code & 63u);
     const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
     const SpanChild* K = ch + c;
@@ -290,9 +318,100 @@ __device__ __noinline__ unsigned int span_settle(const RenderParams& P, const un
     SpanRange r;
     unsigned int bits = 0u, near_lo = 0u, near_hi = 0u, dummy = 0u;
     e_in = e_out = 0u;
-    if (!span_candidate_range(*H, *K, *ray, *R0, px, py, pz, deg_axis, r, bits)) return bits;
+    if (!span_candidate_range<true>(*H, *K, *ray, *R0, px, py, pz, skip_axes, r, bits)) return 0u;  // (surely outside some constraint)
+    if (bits & 0xfeu) return bits & 0xffu;  // a case that is not settled here (a thin slab, a non-monotone plane constraint, ...)
+    // bit 0 is flagged again (that is why we are here) and bits 8.. count the undecided constraints
+    if (!fuzzy) bits = 0u;
     const double sc = P.s_center;
+    const double dx = ray->dx, dy = ray->dy, dz = ray->dz;
     const bool sure = r.L1 <= r.U0;
+    auto member = [&](unsigned int e) { return span_exact_member<INTEG>(P, nfine, H, K, eye, dx, dy, dz, e, px, py, pz); };
+    if (fuzzy) {
+        bits &= ~0xffu;
+        // The ray runs inside a bounding plane of this child (span_slab): that constraint was left out of r.  Along the ray it
+        // is a step function of the ordinal (monotone expressions: span_mixed cases never get here), so the members are the
+        // ordinals of one interval still.  Core = the ordinals surely inside every other constraint: its members are found
+        // from its two ends and a bisection; the doubt zones either side are looked at sample by sample.
+        unsigned int e0 = max(span_ordinal_after<INTEG>(P, nfine, r.L0 + sc, 0.0, inv_ds, inv_dsf, dummy), e_first);
+        unsigned int e1 = min(span_ordinal_after<INTEG>(P, nfine, r.U1 + sc, 0.0, inv_ds, inv_dsf, dummy), e_last);
+        if (e0 >= e1) return bits;
+        // first member in [from, to) and the first non-member after it (to if none); false when the guard trips
+        auto scan_run = [&](unsigned int from, unsigned int to, unsigned int& lo, unsigned int& hi) -> bool {
+            int guard = 0;
+            unsigned int e = from;
+            while (e < to && !member(e)) {
+                e = span_next_ordinal<INTEG>(nfine, e);
+                if (++guard > 24) return false;
+            }
+            lo = e;
+            while (e < to && member(e)) {
+                e = span_next_ordinal<INTEG>(nfine, e);
+                if (++guard > 48) return false;
+            }
+            hi = e;
+            return true;
+        };
+        unsigned int a = e0, b = e0;  // the core [a, b)
+        if (sure) {
+            a = min(max(span_ordinal_after<INTEG>(P, nfine, r.L1 + sc + 1.0e-13, 0.0, inv_ds, inv_dsf, dummy), e0), e1);
+            // ordinals at positions < U0: up to (not including) the first ordinal at a position > U0 - tiny
+            b = min(max(span_ordinal_after<INTEG>(P, nfine, r.U0 + sc - 1.0e-13, 0.0, inv_ds, inv_dsf, dummy), a), e1);
+            while (b > a && span_exact_pos<INTEG>(P, nfine, span_prev_ordinal<INTEG>(nfine, b)) >= r.U0 + sc - 1.0e-13) b = span_prev_ordinal<INTEG>(nfine, b);
+        }
+        unsigned int lo = 0u, hi = 0u;
+        if (a >= b) {  // no lattice sample in the core: the zones hold a handful at most
+            if (!scan_run(e0, e1, lo, hi)) return bits | 4u;
+            e_in = lo;
+            e_out = hi;
+            return bits;
+        }
+        const unsigned int last = span_prev_ordinal<INTEG>(nfine, b);
+        const bool mA = member(a), mB = member(last);
+        if (!mA && !mB) {
+            // One undecided constraint: a step function that is false at both ends of the core is false all over it.  Two
+            // (a ray along an edge) can leave members in the middle: not settled here.
+            if ((bits >> 8) != 1u) return (bits & 0xffu) | 2u;
+            if (!scan_run(e0, a, lo, hi)) return bits | 4u;  // members, if any, sit in one of the zones
+            if (lo >= hi && !scan_run(b, e1, lo, hi)) return bits | 4u;
+            e_in = lo;
+            e_out = hi;
+            return bits;
+        }
+        lo = a;
+        hi = b;
+        if (mA != mB) {
+            unsigned int u = a, v = last;  // member(u) != member(v): bisect for the step
+            while (v - u > 1u) {
+                const unsigned int m = u + ((v - u) >> 1);
+                if (member(m) == mA) u = m;
+                else v = m;
+            }
+            // (ordinals 16 k + j with j beyond the interval's fine samples evaluate as its coarse sample, 16 k + 15)
+            if (INTEG == 1 && (v & 15u) != 15u && ((v & 15u) == 0u || (v & 15u) > (unsigned int)__ldg(nfine + (v >> 4)))) {
+                v = (v & 15u) == 0u ? v + 1u : (v & ~15u) + 15u;
+                if ((v & 15u) == 1u && __ldg(nfine + (v >> 4)) == 0) v = (v & ~15u) + 15u;
+            }
+            if (mA) hi = v;
+            else lo = v;
+        }
+        if (lo == a && e0 < a) {  // the lower zone: first member there, if any
+            unsigned int zl = 0u, zh = 0u;
+            if (!scan_run(e0, a, zl, zh)) return bits | 4u;
+            if (zl < a) lo = zl;
+        }
+        if (hi == b && b < e1) {  // the upper zone: members directly after the core
+            unsigned int e = b;
+            int guard = 0;
+            while (e < e1 && member(e)) {
+                e = span_next_ordinal<INTEG>(nfine, e);
+                if (++guard > 24) return bits | 4u;
+            }
+            hi = e;
+        }
+        e_in = lo;
+        e_out = hi;
+        return bits;
+    }
     if (sure) {
         e_in = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.L1) + sc, 0.5 * (r.L1 - r.L0), inv_ds, inv_dsf, near_lo);
         e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.U0 + r.U1) + sc, 0.5 * (r.U1 - r.U0), inv_ds, inv_dsf, near_hi);
@@ -300,13 +419,12 @@ __device__ __noinline__ unsigned int span_settle(const RenderParams& P, const un
         e_in = e_out = span_ordinal_after<INTEG>(P, nfine, 0.5 * (r.L0 + r.U1) + sc, 0.5 * (r.U1 - r.L0), inv_ds, inv_dsf, near_lo);
         near_hi = near_lo;
     }
-    const double dx = ray->dx, dy = ray->dy, dz = ray->dz;
     if (near_lo) {
-        unsigned int e = span_ordinal_after<INTEG>(P, nfine, r.L0 + sc, 0.0, inv_ds, inv_dsf, dummy);  // first sample beyond L0
+        unsigned int e = max(span_ordinal_after<INTEG>(P, nfine, r.L0 + sc, 0.0, inv_ds, inv_dsf, dummy), e_first);  // first sample beyond L0
         const double stop = (sure ? r.L1 : r.U1) + sc + 1.0e-13;
         int guard = 0;
         while (e < e_last && span_exact_pos<INTEG>(P, nfine, e) <= stop) {
-            if (span_exact_member<INTEG>(P, nfine, H, K, eye, dx, dy, dz, e, px, py, pz)) break;
+            if (member(e)) break;
             e = span_next_ordinal<INTEG>(nfine, e);
             if (++guard > 12) {
                 bits |= 4u;
@@ -318,11 +436,11 @@ __device__ __noinline__ unsigned int span_settle(const RenderParams& P, const un
     }
     if (near_hi) {
         unsigned int e = sure ? span_ordinal_after<INTEG>(P, nfine, r.U0 + sc, 0.0, inv_ds, inv_dsf, dummy) : e_out;
-        if (e < e_in) e = e_in;
+        e = max(max(e, e_in), e_first);  // (e_first: samples before it fold into another period along a degenerate axis)
         const double stop = r.U1 + sc + 1.0e-13;
         int guard = 0;
         while (e < e_last && span_exact_pos<INTEG>(P, nfine, e) <= stop) {
-            if (!span_exact_member<INTEG>(P, nfine, H, K, eye, dx, dy, dz, e, px, py, pz)) break;
+            if (!member(e)) break;
             e = span_next_ordinal<INTEG>(nfine, e);
             if (++guard > 12) {
                 bits |= 4u;
@@ -416,7 +534,9 @@ __device__ __forceinline__ double span_combine(const SpanChild* __restrict__ ch,
 // flags its warp tile for the settle pass.  SETTLE = true: the same code over the flagged warp tiles, with the exact settling
 // of those samples compiled in (span_settle; it costs the hot loop 15 % in registers and stack traffic, so the fast pass
 // does not carry it).  Whatever neither pass can vouch for goes to the marching kernels.
-template <int INTEG, bool COUNT, bool SETTLE>
+// WALK = false (fast pass of a launch with screen-space bins): the grid walk is not compiled in -- it costs the binned hot
+// loop 3-7 % in registers -- and the few tiles whose bin overflowed are left to the settle pass, which always has it.
+template <int INTEG, bool COUNT, bool SETTLE, bool WALK>
 __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_kernel(const RenderParams P, const unsigned char* __restrict__ nfine,
                                                                        const SpanArgs SA) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -482,12 +602,15 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
     hit = hit && span_slab(cy, dy, idy, H.outer[1], H.outer[4], epsx, R0, doubt);
     hit = hit && span_slab(cz, dz, idz, H.outer[2], H.outer[5], epsx, R0, doubt);
     if (!valid) doubt = 0u;
+    // A ray inside a face of the outer box: every sample's outer test is undecided (TESS: left to the marching kernels);
+    // the region of a flat collection is only a bound of ours, the children decide for themselves.
+    if (doubt) doubt = tess ? 2u : 0u;
     const double ta = R0.L0, tb = R0.U1;
     const double inv_ds = 1.0 / P.ds, inv_dsf = 1.0 / P.ds_fine;
 
     // ---- a ray inside a cell-face plane of the tessellation: exact period per sample along that axis ----
-    int deg_axis = -1, deg_m = 0;
-    SpanDegenerate dg = {0, 0, 0u, 0u, 0u};
+    int deg_axis = -1, deg_axis2 = -1, deg_m = 0, skip_axes = 0;
+    SpanDegenerate dg = {0, 0, 0u, 0u, 0u}, dg2 = {0, 0, 0u, 0u, 0u};
     if (tess) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -495,10 +618,18 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             if (hit && fabs(da) < 1.0e-9) {
                 const double q = (ca - H.uc_lo[a]) / H.uc_d[a], m = rint(q);
                 if (fabs(q - m) * fabs(H.uc_d[a]) < 6.0e-9 + epsx) {
-                    if (deg_axis >= 0 || (flags & SPAN_HAS_WARP)) doubt |= 8u;  // two such axes, or a warp between ray and fold
-                    else {
+                    if (flags & SPAN_HAS_WARP) doubt |= 8u;  // a warp between the ray and the fold: not settled here
+                    else if (deg_axis >= 0) {  // a second such axis (a ray along a cell edge): the settle pass gives it the same
+                        if (SETTLE && SA.bin_counts) {  // treatment; it takes its candidates from the tile's bin
+                            deg_axis2 = a;
+                            skip_axes |= 1 << a;
+                        } else {
+                            doubt |= 8u;
+                        }
+                    } else {
                         deg_axis = a;
                         deg_m = (int)m;
+                        skip_axes |= 1 << a;
                     }
                 }
             }
@@ -513,7 +644,50 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             const bool ok = span_degenerate_axis<INTEG>(P, nfine, P.cams[view].eye[a], da, H.uc_lo[a], H.uc_hi[a], H.uc_d[a], dg);
             if (deg_axis >= 0 && !ok) doubt |= 16u;
         }
+        if (SETTLE && __any_sync(FULL_MASK, deg_axis2 >= 0)) {
+            dg2.eA = dg.eA;
+            dg2.eB = dg.eB;
+            const int a = max(deg_axis2, 0);
+            const double da = a == 0 ? dx : (a == 1 ? dy : dz);
+            const bool ok = span_degenerate_axis<INTEG>(P, nfine, P.cams[view].eye[a], da, H.uc_lo[a], H.uc_hi[a], H.uc_d[a], dg2);
+            if (deg_axis2 >= 0 && !ok) doubt |= 16u;
+        }
     }
+#ifdef XRAY_DEV_KNOBS
+    const bool dbg_px = P.dbg_cause >= 1000000 && i == (P.dbg_cause - 1000000) / 1000 && j == (P.dbg_cause % 1000) && valid;
+    if (dbg_px)
+        printf("[span %d] px (%d,%d) c (%.17g %.17g %.17g) d (%.17g %.17g %.17g) hit %d doubt %u R0 [%g %g %g %g] deg %d %d skip %d dg n %d %d e %u %u sw %u dg2 n %d %d sw %u\n",
+               (int)SETTLE, i, j, cx, cy, cz, dx, dy, dz, (int)hit, doubt, R0.L0, R0.L1, R0.U0, R0.U1, deg_axis, deg_axis2, skip_axes, dg.nA, dg.nB, dg.eA,
+               dg.eB, dg.e_sw, dg2.nA, dg2.nB, dg2.e_sw);
+#endif
+    // ordinal window of a period along the degenerate axes; false = the ray never folds into that period
+    auto deg_window = [&](int px, int py, int pz, unsigned int& w_lo, unsigned int& w_hi) -> bool {
+        if (deg_axis >= 0) {
+            const int pa = deg_axis == 0 ? px : (deg_axis == 1 ? py : pz);
+            if (pa == dg.nA) {
+                w_lo = max(w_lo, dg.eA);
+                w_hi = min(w_hi, dg.nA == dg.nB ? dg.eB : dg.e_sw);
+            } else if (pa == dg.nB) {
+                w_lo = max(w_lo, dg.e_sw);
+                w_hi = min(w_hi, dg.eB);
+            } else {
+                return false;
+            }
+        }
+        if (SETTLE && deg_axis2 >= 0) {
+            const int pa = deg_axis2 == 0 ? px : (deg_axis2 == 1 ? py : pz);
+            if (pa == dg2.nA) {
+                w_lo = max(w_lo, dg2.eA);
+                w_hi = min(w_hi, dg2.nA == dg2.nB ? dg2.eB : dg2.e_sw);
+            } else if (pa == dg2.nB) {
+                w_lo = max(w_lo, dg2.e_sw);
+                w_hi = min(w_hi, dg2.eB);
+            } else {
+                return false;
+            }
+        }
+        return true;
+    };
 
     // ---- phase 1: candidates.  Either the tile's screen-space bin (one list per 8 x 16 pixel tile, built per launch by
     // span_bin_kernel) or, without one, an fp32 walk of this ray through the candidate grid.  Either way every candidate
@@ -542,11 +716,11 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         } else {  // the sphere itself / the bounding sphere of a box or parallelepiped, inflated
             C -= K.f[3];
         }
-        const float disc = B * B - A * C;
-        if (disc < -2.0e-6f * (1.0f + B * B)) pass = false;
-        else {
-            const float iA = 1.0f / fmaxf(A, 1.0e-12f);
-            const float th = sqrtf(fmaxf(disc, 0.0f)) * iA + 1.0e-3f, tm = -B * iA;
+        const float disc = B * B - A * C, tol = 2.0e-6f * (1.0f + B * B);
+        if (disc < -tol) pass = false;
+        else if (A > 1.0e-3f * fA) {  // (a ray within 2 degrees of a cylinder's axis: A and B are rounding noise in fp32 -- no range test)
+            const float iA = 1.0f / A;
+            const float th = sqrtf(disc + tol) * iA + 1.0e-3f, tm = -B * iA;
             if (tm + th < fta || tm - th > ftb) pass = false;
             if (K.type == OP_CYL) {
                 const float cm = (wv + tm * dv) * ivv, hc = th * fabsf(dv) * ivv + 1.0e-3f;
@@ -564,7 +738,11 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
     const unsigned int* __restrict__ bl = nullptr;
     if (SA.bin_counts) {  // uniform
         nb = __ldg(SA.bin_counts + (item >> 2));
-        if (nb <= SA.bin_cap) {  // (a bin that overflowed is not used: those tiles walk)
+        if (!WALK && nb > SA.bin_cap) {  // (a bin that overflowed is not used: those tiles walk -- in the settle pass)
+            walk = false;
+            if (hit) doubt |= 64u;
+        }
+        if (nb <= SA.bin_cap) {
             walk = false;
             bl = SA.bin_lists + (size_t)(item >> 2) * SA.bin_cap;
             const float ucdx = (float)H.uc_d[0], ucdy = (float)H.uc_d[1], ucdz = (float)H.uc_d[2];
@@ -576,16 +754,27 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
                     const int pa = deg_axis == 0 ? px : (deg_axis == 1 ? py : pz);
                     if (pa != dg.nA && pa != dg.nB) continue;
                 }
+                if (SETTLE && deg_axis2 >= 0) {
+                    const int pa = deg_axis2 == 0 ? px : (deg_axis2 == 1 ? py : pz);
+                    if (pa != dg2.nA && pa != dg2.nB) continue;
+                }
                 if (hit)
                     test_and_push((int)(code & 63u), (int)(code & ~63u), fcx - (float)px * ucdx + ulx, fcy - (float)py * ucdy + uly,
                                   fcz - (float)pz * ucdz + ulz);
             }
         }
     }
-    const int n_pass = walk ? (deg_axis >= 0 ? 2 : 1) : 0;  // a ray inside a face plane walks the cells on either side of it
-    const int max_pass = __reduce_max_sync(FULL_MASK, n_pass);
+    if (SETTLE && deg_axis2 >= 0 && bl == nullptr) doubt |= 8u;  // (the walk knows one such axis only)
+#ifdef XRAY_DEV_KNOBS
+    if (dbg_px) printf("[span %d] bins: nb %u bl %d ncand %d overflow %d\n", (int)SETTLE, nb, (int)(bl != nullptr), ncand, (int)overflow);
+#endif
+    // The walk runs in fp32 (position error a few 1e-6) while the exact ray may sit on the other side of a cell face -- for good,
+    // when it runs inside or alongside one.  So every stretch of the walk also visits the neighbours whose face the fp32
+    // position comes closer to than tie_d (side cells; across a period boundary that is the neighbouring period's cell,
+    // whose children the dilated masks of this side do not list).
+    const int max_pass = (WALK && __any_sync(FULL_MASK, walk)) ? 1 : 0;
     for (int pass = 0; pass < max_pass; ++pass) {
-        if (pass >= n_pass) continue;
+        if (!walk) continue;
         const int gx = (int)H.g[0], gy = (int)H.g[1], gz = (int)H.g[2];
         const float icx = H.f_inv_cell[0], icy = H.f_inv_cell[1], icz = H.f_inv_cell[2];
         const float csx = H.f_cell[0], csy = H.f_cell[1], csz = H.f_cell[2];
@@ -597,25 +786,31 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         int ix = __float2int_rd(fmaf(fdx, t_begin, fcx) * icx), iy = __float2int_rd(fmaf(fdy, t_begin, fcy) * icy),
             iz = __float2int_rd(fmaf(fdz, t_begin, fcz) * icz);
         const int sx = fdx > 0.0f ? 1 : -1, sy = fdy > 0.0f ? 1 : -1, sz = fdz > 0.0f ? 1 : -1;
-        if (deg_axis == 0) ix = deg_m * gx - 1 + pass;  // last cell of period m - 1, then first cell of period m
-        if (deg_axis == 1) iy = deg_m * gy - 1 + pass;
-        if (deg_axis == 2) iz = deg_m * gz - 1 + pass;
+        if (deg_axis == 0) ix = deg_m * gx;  // first cell of period m: the ray runs inside its lower face (the side visits take the other side)
+        if (deg_axis == 1) iy = deg_m * gy;
+        if (deg_axis == 2) iz = deg_m * gz;
         const float tie_d = 0.25f * slack;
-        unsigned long long done = 0ull;
+        // children already pushed, per period: the period the walk is in, and up to three neighbouring ones seen by side visits
+        // (a child pushed twice would only yield the same interval twice, but a ray that runs along a face would do that at every step)
+        unsigned long long done = 0ull, done1 = 0ull, done2 = 0ull, done3 = 0ull;
+        int main_code = -1, key1 = -1, key2 = -1, key3 = -1, slot = 0;
 
-        // visit one grid cell (local index l*, period p*): new children of its mask are pre-filtered and pushed
-        // (`done` = the children already seen in the current period; the walk clears it when it enters another period.  The
-        // rare extra cells of a near-tie are visited with `side` set: they may belong to a neighbouring period, so they
-        // neither read nor update it -- a child pushed twice just yields the same interval twice.)
-        auto visit = [&](int lx, int ly, int lz, int px, int py, int pz, bool side) {
+        auto visit = [&](int lx, int ly, int lz, int px, int py, int pz) {
             if (!tess && (px | py | pz) != 0) return;  // outside the region
             unsigned long long nw = masks[(lz * gy + ly) * gx + lx];
-            if (!side) {
-                nw &= ~done;
-                done |= nw;
-            }
             if (nw == 0ull) return;
             const int pcode = ((px + 16) << 6) | ((py + 16) << 11) | ((pz + 16) << 16);  // |p| <= 15: scene_compile.cpp build_span
+            if (pcode == main_code) { nw &= ~done; done |= nw; }
+            else if (pcode == key1) { nw &= ~done1; done1 |= nw; }
+            else if (pcode == key2) { nw &= ~done2; done2 |= nw; }
+            else if (pcode == key3) { nw &= ~done3; done3 |= nw; }
+            else {
+                if (slot == 0) { key1 = pcode; done1 = nw; }
+                else if (slot == 1) { key2 = pcode; done2 = nw; }
+                else { key3 = pcode; done3 = nw; }
+                slot = slot == 2 ? 0 : slot + 1;
+            }
+            if (nw == 0ull) return;
             // ray centre relative to this period's copy of the cell
             const float qx = fcx - (float)px * ucdx + ulx, qy = fcy - (float)py * ucdy + uly, qz = fcz - (float)pz * ucdz + ulz;
             while (nw) {
@@ -629,6 +824,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         int px = __float2int_rd(((float)ix + 0.5f) / (float)gx), py = __float2int_rd(((float)iy + 0.5f) / (float)gy),
             pz = __float2int_rd(((float)iz + 0.5f) / (float)gz);
         int lx = ix - px * gx, ly = iy - py * gy, lz = iz - pz * gz;
+        main_code = ((px + 16) << 6) | ((py + 16) << 11) | ((pz + 16) << 16);
         // parameter at which the ray leaves the cell along each axis, from the absolute cell index (no drift)
         // (an axis the ray does not move along -- exactly, or to 1e-9 inside a face plane -- is never stepped)
         float tx = (fdx != 0.0f && deg_axis != 0) ? (((float)(ix + (sx > 0 ? 1 : 0))) * csx - fcx) * ifx : 3.0e38f;
@@ -637,46 +833,70 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         // two faces count as reached together when the second is closer than tie_d (in space) at that moment
         const float hx = (fdx != 0.0f && deg_axis != 0) ? tie_d * fabsf(ifx) : 0.0f, hy = (fdy != 0.0f && deg_axis != 1) ? tie_d * fabsf(ify) : 0.0f,
                     hz = (fdz != 0.0f && deg_axis != 2) ? tie_d * fabsf(ifz) : 0.0f;
-        const float hmax = fmaxf(hx, fmaxf(hy, hz));
+        float t_prev = t_begin;
         for (int guard = 0; guard < 4096; ++guard) {
-            visit(lx, ly, lz, px, py, pz, false);
+            visit(lx, ly, lz, px, py, pz);
             const float tm = fminf(tx, fminf(ty, tz));
+            // the stretch [t_prev, tm] of the ray against the faces of this cell
+            {
+                const float te = fminf(tm, t_end);
+                const float x0 = fmaf(fdx, t_prev, fcx), x1 = fmaf(fdx, te, fcx), y0 = fmaf(fdy, t_prev, fcy), y1 = fmaf(fdy, te, fcy),
+                            z0 = fmaf(fdz, t_prev, fcz), z1 = fmaf(fdz, te, fcz);
+                const float lox = (float)ix * csx, loy = (float)iy * csy, loz = (float)iz * csz;
+                const int mx = fminf(x0, x1) - lox < tie_d ? -1 : 0, Mx = lox + csx - fmaxf(x0, x1) < tie_d ? 1 : 0;
+                const int my = fminf(y0, y1) - loy < tie_d ? -1 : 0, My = loy + csy - fmaxf(y0, y1) < tie_d ? 1 : 0;
+                const int mz = fminf(z0, z1) - loz < tie_d ? -1 : 0, Mz = loz + csz - fmaxf(z0, z1) < tie_d ? 1 : 0;
+                if ((mx | Mx | my | My | mz | Mz) != 0) {
+                    for (int oz = mz; oz <= Mz; ++oz)
+                        for (int oy = my; oy <= My; ++oy)
+                            for (int ox = mx; ox <= Mx; ++ox) {
+                                if ((ox | oy | oz) == 0) continue;
+                                int vx = lx + ox, vy = ly + oy, vz = lz + oz, qx = px, qy = py, qz = pz;
+                                if (vx == gx) { vx = 0; ++qx; } else if (vx < 0) { vx = gx - 1; --qx; }
+                                if (vy == gy) { vy = 0; ++qy; } else if (vy < 0) { vy = gy - 1; --qy; }
+                                if (vz == gz) { vz = 0; ++qz; } else if (vz < 0) { vz = gz - 1; --qz; }
+                                visit(vx, vy, vz, qx, qy, qz);
+                            }
+                }
+            }
             if (!(tm <= t_end)) break;
             const bool nx = tx - tm < hx, ny = ty - tm < hy, nz = tz - tm < hz;
-            if (fmaxf(fminf(tx, ty), fminf(fmaxf(tx, ty), tz)) - tm < hmax) {  // the second face is near: look closer
-              if ((nx ? 1 : 0) + (ny ? 1 : 0) + (nz ? 1 : 0) > 1) {
-                // the exact ray may cross these faces in another order: visit every cell of the little block between here
-                // and the far corner (the far corner itself is the next regular visit)
-                for (int m = 1; m < 7; ++m) {
-                    const bool bx = m & 1, by = m & 2, bz = m & 4;
-                    if ((bx && !nx) || (by && !ny) || (bz && !nz)) continue;
-                    if (bx == nx && by == ny && bz == nz) continue;
-                    int vx = lx + (bx ? sx : 0), vy = ly + (by ? sy : 0), vz = lz + (bz ? sz : 0), qx = px, qy = py, qz = pz;
-                    if (vx == gx) { vx = 0; ++qx; } else if (vx < 0) { vx = gx - 1; --qx; }
-                    if (vy == gy) { vy = 0; ++qy; } else if (vy < 0) { vy = gy - 1; --qy; }
-                    if (vz == gz) { vz = 0; ++qz; } else if (vz < 0) { vz = gz - 1; --qz; }
-                    visit(vx, vy, vz, qx, qy, qz, true);
-                }
-              }
-            }
+            bool moved = false;  // into another period
             if (nx) {
                 ix += sx;
                 lx += sx;
-                if (lx == gx) { lx = 0; ++px; done = 0ull; } else if (lx < 0) { lx = gx - 1; --px; done = 0ull; }
+                if (lx == gx) { lx = 0; ++px; moved = true; } else if (lx < 0) { lx = gx - 1; --px; moved = true; }
                 tx = (((float)(ix + (sx > 0 ? 1 : 0))) * csx - fcx) * ifx;
             }
             if (ny) {
                 iy += sy;
                 ly += sy;
-                if (ly == gy) { ly = 0; ++py; done = 0ull; } else if (ly < 0) { ly = gy - 1; --py; done = 0ull; }
+                if (ly == gy) { ly = 0; ++py; moved = true; } else if (ly < 0) { ly = gy - 1; --py; moved = true; }
                 ty = (((float)(iy + (sy > 0 ? 1 : 0))) * csy - fcy) * ify;
             }
             if (nz) {
                 iz += sz;
                 lz += sz;
-                if (lz == gz) { lz = 0; ++pz; done = 0ull; } else if (lz < 0) { lz = gz - 1; --pz; done = 0ull; }
+                if (lz == gz) { lz = 0; ++pz; moved = true; } else if (lz < 0) { lz = gz - 1; --pz; moved = true; }
                 tz = (((float)(iz + (sz > 0 ? 1 : 0))) * csz - fcz) * ifz;
             }
+            if (moved) {  // keep what is known about the period walked into, if a side visit has seen it
+                const int nc = ((px + 16) << 6) | ((py + 16) << 11) | ((pz + 16) << 16);
+                const unsigned long long keep = nc == key1 ? done1 : (nc == key2 ? done2 : (nc == key3 ? done3 : 0ull));
+                // the period left behind takes that slot (or the next one to be replaced)
+                if (nc == key1) { key1 = main_code; done1 = done; }
+                else if (nc == key2) { key2 = main_code; done2 = done; }
+                else if (nc == key3) { key3 = main_code; done3 = done; }
+                else {
+                    if (slot == 0) { key1 = main_code; done1 = done; }
+                    else if (slot == 1) { key2 = main_code; done2 = done; }
+                    else { key3 = main_code; done3 = done; }
+                    slot = slot == 2 ? 0 : slot + 1;
+                }
+                main_code = nc;
+                done = keep;
+            }
+            t_prev = tm;
             if (guard == 4095) overflow = true;
         }
     }
@@ -731,21 +951,24 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         const int px = (int)((code >> 6) & 31u) - 16, py = (int)((code >> 11) & 31u) - 16, pz = (int)((code >> 16) & 31u) - 16;
         if (COUNT) ++prim_tests;
         unsigned int w_lo = e_first, w_hi = e_last;  // ordinal window of this period along a degenerate axis
-        if (deg_axis >= 0) {
-            const int pa = deg_axis == 0 ? px : (deg_axis == 1 ? py : pz);
-            if (pa == dg.nA) {
-                w_lo = dg.eA;
-                w_hi = dg.nA == dg.nB ? dg.eB : dg.e_sw;
-            } else if (pa == dg.nB) {
-                w_lo = dg.e_sw;
-                w_hi = dg.eB;
-            } else {
-                continue;
-            }
-        }
+        if (!deg_window(px, py, pz, w_lo, w_hi)) continue;
         const SpanChild& K = ch[c];
         SpanRange r;
-        if (!span_candidate_range(H, K, ray, R0, px, py, pz, deg_axis, r, doubt)) continue;
+        if (SETTLE) {
+            unsigned int cb = 0u;  // this candidate's doubts
+            const bool some = span_candidate_range<true>(H, K, ray, R0, px, py, pz, skip_axes, r, cb);
+            if (some && (cb & 0xffu) == 1u && nfz < kSpanFuzzCap) {  // the ray runs inside a plane of this child: settled below
+                fuzz[(nfz++) * kBlockThreads + tid] = code | 0x80000000u;
+                continue;
+            }
+            doubt |= cb & 0xffu;
+            if (!some) continue;
+        } else {  // (the fast pass only flags; bits 8.. of doubt are masked off at the end)
+            if (!span_candidate_range<false>(H, K, ray, R0, px, py, pz, skip_axes, r, doubt)) continue;
+        }
+#ifdef XRAY_DEV_KNOBS
+        if (dbg_px) printf("[span %d]   cand c %d p (%d %d %d) w [%u %u) r [%.12g %.12g %.12g %.12g] doubt %u\n", (int)SETTLE, c, px, py, pz, w_lo, w_hi, r.L0, r.L1, r.U0, r.U1, doubt);
+#endif
         // End points -> lattice ordinals.  Common case: no lattice sample lies inside either doubt zone.  A candidate with one
         // that does is set aside (fuzz list) and settled after this loop, sample by sample, with the reference's own expressions.
         const double sc = P.s_center;
@@ -777,15 +1000,17 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
         for (int f = 0; f < nfz; ++f) {
             const unsigned int code = fuzz[f * kBlockThreads + tid];
             unsigned int e_in = 0u, e_out = 0u;
-            doubt |= span_settle<INTEG>(P, nfine, &H, ch, P.cams[view].eye, &ray, &R0, code, deg_axis, e_last, e_in, e_out);
-            if (deg_axis >= 0) {
-                const int pa = (int)((code >> (deg_axis == 0 ? 6 : (deg_axis == 1 ? 11 : 16))) & 31u) - 16;
-                const unsigned int w_lo = pa == dg.nA ? dg.eA : dg.e_sw, w_hi = (pa == dg.nA && dg.nA != dg.nB) ? dg.e_sw : dg.eB;
-                e_in = max(w_lo, e_in);
-                e_out = min(w_hi, e_out);
-            }
-            e_in = max(win_lo, e_in);
-            e_out = min(win_hi, e_out);
+            // the ordinals in which the ray folds into this candidate's period along the degenerate axes (span_settle's
+            // bisection needs that settled: inside this range only the plane constraint can step), and the lattice window
+            unsigned int w_lo = win_lo, w_hi = win_hi;
+            deg_window((int)((code >> 6) & 31u) - 16, (int)((code >> 11) & 31u) - 16, (int)((code >> 16) & 31u) - 16, w_lo, w_hi);
+            if (w_lo >= w_hi) continue;
+            doubt |= span_settle<INTEG>(P, nfine, &H, ch, P.cams[view].eye, &ray, &R0, code, skip_axes, w_lo, w_hi, e_in, e_out) & 0xffu;
+#ifdef XRAY_DEV_KNOBS
+            if (dbg_px) printf("[span]   settled code %x w [%u %u) -> [%u %u) doubt %u\n", code, w_lo, w_hi, e_in, e_out, doubt);
+#endif
+            e_in = max(w_lo, e_in);
+            e_out = min(w_hi, e_out);
             if (e_in >= e_out) continue;
             if (niv < cap) {
                 iv_in[niv * kBlockThreads + tid] = e_in | ((code & 63u) << 26);
@@ -874,11 +1099,12 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
     overflow = false;
     }  // attempts
     if (overflow) doubt |= 32u;
+    doubt &= 0xffu;
     const bool bad = valid && doubt != 0u;
     const bool tile_bad = __any_sync(FULL_MASK, bad);
     // fast pass: a warp tile whose only trouble is samples inside doubt zones goes to the settle pass, not to the marching kernels
     // (samples inside doubt zones; more intervals than the list holds, when the tile has a bin to take the candidates from)
-    const bool settleable = (doubt & ~(4u | 32u)) == 0u && (!(doubt & 32u) || bl != nullptr);
+    const bool settleable = (doubt & ~(1u | 4u | 8u | 32u | 64u)) == 0u && (!(doubt & (8u | 32u)) || bl != nullptr);
     const bool to_settle = !SETTLE && !(flags & SPAN_HAS_WARP) && tile_bad && !__any_sync(FULL_MASK, bad && !settleable);
     if ((tid & 31) == 0 && tile_bad) {
         if (to_settle) {
@@ -888,7 +1114,7 @@ __global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_
             if (COUNT && P.stats) atomicAdd(P.stats + 6, 1ull);  // warp tiles handed to the marching kernels
         }
     }
-    if (COUNT && P.stats && bad && !to_settle) atomicOr(P.stats + 7, (unsigned long long)doubt);
+    if (COUNT && P.stats && bad && !to_settle) atomicOr(P.stats + 7, (unsigned long long)(doubt & 0x3fu));
 #ifdef XRAY_DEV_KNOBS
     if (P.dbg_cause == 77) {  // development builds: show which rays are handed over, and why
         store_pixel(P, view, i, j, valid, bad && !to_settle ? -(double)doubt : exp(-(P.flat_field + T)));
@@ -1013,8 +1239,8 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
     const unsigned int grid_settle = (unsigned int)(tiles < (size_t)sms ? tiles : (size_t)sms);
 #define XR_SGO(I, C)                                                                                                        \
     do {                                                                                                                    \
-        auto fast = render_span_kernel<I, C, false>;                                                                        \
-        auto settle = render_span_kernel<I, C, true>;                                                                       \
+        auto fast = SA.bin_counts ? render_span_kernel<I, C, false, false> : render_span_kernel<I, C, false, true>;         \
+        auto settle = render_span_kernel<I, C, true, true>;                                                                 \
         cudaError_t e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);            \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(settle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_settle); \
         if (e != cudaSuccess) return e;                                                                                     \
