@@ -154,6 +154,29 @@ def test_rays_along_cell_edges_of_a_tessellation(X, O, scenes):
     _check(X, O, str(scenes / "lattice.json"), views=((0.0, 90.0), (90.0, 90.0)), res=64, max_marched=2)
 
 
+@pytest.mark.parametrize("bins", [True, False])
+@pytest.mark.parametrize("tilt", [1e-4, 1e-6, 3e-8, 1e-10])
+def test_rays_alongside_cell_faces(X, O, scenes, monkeypatch, bins, tilt):
+    """Views a hair (1e-4 ... 1e-10 degrees) off the axes: whole pixel rows run ALONGSIDE a cell face of the tessellation --
+    within 1e-6 ... 1e-12 of it for the whole length, on one side first and the other later -- without being inside it to
+    1e-9.  The fp32 candidate walk (tiles without a usable screen-space bin; XRAY_SPAN_NO_BINS forces it everywhere) must
+    still find the children on the exact ray's side of the face, and rays nearly parallel to a strut's axis must survive the
+    fp32 pre-filter."""
+    if not bins:
+        monkeypatch.setenv("XRAY_SPAN_NO_BINS", "1")
+    uc = {"objects": {"objects": [{"type": "sphere", "center": [0.0, 0.0, 0.0], "radius": 0.12, "rho": 0.9},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.3, 0.0, 0.0], "radius": 0.04, "rho": 0.5},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.0, 0.3, 0.0], "radius": 0.05, "rho": 0.4},
+                                  {"type": "cylinder", "p0": [0.0, 0.0, 0.0], "p1": [0.0, 0.0, 0.3], "radius": 0.03, "rho": 0.3},
+                                  {"type": "box", "center": [0.15, 0.0, 0.3], "sides": [0.1, 0.1, 0.1], "rho": 0.7}]},
+          "xmin": 0.0, "xmax": 0.3, "ymin": 0.0, "ymax": 0.3, "zmin": 0.0, "zmax": 0.3}
+    obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.75, "xmax": 0.75, "ymin": -0.6, "ymax": 0.6, "zmin": -0.45, "zmax": 0.9}
+    views = ((tilt, 90.0), (90.0 - tilt, 90.0), (180.0, 90.0 + tilt), (270.0 + tilt, 90.0 - tilt), (0.0, tilt), (45.0, 180.0 - tilt))
+    _check(X, O, obj, views=views, res=32, ds=0.011)
+    _check(X, O, str(scenes / "lattice.json"), views=views[:3], res=32)
+    _check(X, O, str(scenes / "pillar_array.json"), views=(views[0], views[4]), res=32)
+
+
 def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkeypatch):
     """Full 1024^2 lattice view and a 1024^2 crop-equivalent of the pillar array: interval renderer versus the marching
     kernels, which the 1e-4 gate of the rest of the suite already ties to the oracle; same reference-equivalent sample count."""
@@ -286,3 +309,25 @@ def test_random_convex_scene_special_views(X, O, seed):
     out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=((az, pol),), res=res, integ=integ, ds=ds, ff=float(rng.choice([0.0, 0.1])),
                                  dm=float(rng.choice([1.0, 0.5, 2.0])))
     assert_parity(out, nref)  # (a scene without any positive density is not eligible and takes the marching kernels: fine)
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_random_convex_scene_near_special_views(X, O, seed, monkeypatch):
+    """The same scene generator seen a hair off the special directions (tilts of 1e-3 ... 1e-11 degrees, also straight down the
+    z axis), even detector sizes (central row and column through the origin), half of the cases with the fp32 candidate walk
+    forced (no screen-space bins): rays alongside faces, nearly parallel to axes of cylinders, nearly inside cap planes."""
+    rng = np.random.default_rng(77000 + seed)
+    if rng.random() < 0.5:
+        monkeypatch.setenv("XRAY_SPAN_NO_BINS", "1")
+    obj = _span_scene(rng)
+    deform = _span_warp(rng) if rng.random() < 0.3 else None
+    integ = "hierarchical" if rng.random() < 0.6 else "simple"
+    res = int(rng.choice([16, 32, 48]))
+    ds = float(rng.choice([0.03, 0.02, 0.0125, 0.01, 0.005]))
+    tilt = float(10.0 ** rng.uniform(-11, -3)) * (1 if rng.random() < 0.5 else -1)
+    az = float(rng.choice([0.0, 90.0, 180.0, 270.0, 45.0, 135.0])) + (tilt if rng.random() < 0.7 else 0.0)
+    pol = float(rng.choice([90.0, 90.0, 0.0, 180.0, 45.0])) + (tilt if rng.random() < 0.7 else 0.0)
+    pol = min(max(pol, 1e-12), 180.0 - 1e-12)
+    out, nref, _ = gpu_vs_oracle(X, O, obj, deform, views=((az, pol),), res=res, integ=integ, ds=ds, ff=float(rng.choice([0.0, 0.1])),
+                                 dm=float(rng.choice([1.0, 0.5, 2.0])))
+    assert_parity(out, nref)
