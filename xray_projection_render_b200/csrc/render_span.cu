@@ -15,9 +15,23 @@
 //      it, combined in child order in fp64 exactly as ObjectCollection.Density does (objects.go:422-438).
 // No sample is ever classified in fp32: the only inexact step is the fp64 root of a quadratic, accurate to ~1e-15, and
 // a lattice sample closer than 1e-11 (plus the conditioning of the root) to ANY end point, cell face or bound raises
-// `doubt` for the ray.  Tiles with a doubtful ray (and rays that overflow the small per-ray lists) are flagged and
-// re-rendered by the marching kernels, which settle such samples with the reference's own operation order.  The
-// result therefore equals the marching kernels' to ~1e-15 in T, in both precision modes.
+// `doubt` for the ray.  Three passes share the work:
+//   fast pass    every warp tile; a ray with any doubt only flags its warp tile (no exact arithmetic compiled in);
+//   settle pass  the flagged warp tiles again, with the reference's own expressions in its own operation order for
+//                exactly the samples in doubt: samples inside a doubt zone (span_settle), rays INSIDE a bounding plane of
+//                a child (a monotone step per plane: bisected), rays inside one or two cell-face planes of the tessellation
+//                (span_degenerate_axis: the period step bisected per axis), rays with more intervals than the lists
+//                hold (rendered in windows of the lattice), tiles whose screen-space bin overflowed (grid walk);
+//   hand-over    what neither can vouch for -- two undecided planes at once, a plane constraint whose rounded expression
+//                is not monotone, a ray parallel to and ON a cylinder's surface, a ray inside a face of the outer box, any
+//                of the above under a warp -- is compacted into a list and rendered by the marching kernels.
+// The result therefore equals the marching kernels' to ~1e-15 in T, in both precision modes.
+//
+// Doubt bits (stats[7] reports those of the rays that were handed over): 1 a ray inside a bounding plane (settled unless
+// one of the cases above); 2 not settled here by construction (see hand-over); 4 a lattice sample inside a doubt zone
+// that span_settle could not settle (guards, more than kSpanFuzzCap such candidates); 8 a second cell-face plane (settled
+// when the tile has a bin); 16 the period along a degenerate axis is not a single step; 32 more intervals than the
+// lists hold (settled in windows when the tile has a bin); 64 (internal) bin overflow seen by a fast pass without the walk.
 #include <cstdio>
 #include "eval.cuh"
 
