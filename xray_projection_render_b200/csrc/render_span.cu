@@ -46,6 +46,7 @@ namespace xr {
 // Per-ray list capacity (candidates that survive the pre-filter = intervals at most): whatever fits the shared memory a CTA may
 // use at XR_SPAN_MINBLOCKS CTAs per SM, at most 64.
 constexpr int kSpanCapMax = XR_SPAN_CAPMAX;
+constexpr int kSpanCapDense = 24;  // smallest list capacity worth running 5 CTAs per SM for
 constexpr int kSpanFuzzCap = 4;  // candidates per ray set aside for exact settling
 constexpr double kZone = 1.0e-11; // half-width (in s) of the doubt zone around every end point
 
@@ -63,8 +64,8 @@ struct SpanArgs {
     unsigned int bin_cap;
 };
 
-static int span_list_cap(unsigned int section_bytes, bool with_fuzz) {
-    const size_t budget = (size_t)216 * 1024 / XR_SPAN_MINBLOCKS - 1024;  // 228 KB per SM, 1 KB per CTA reserved, some slack
+static int span_list_cap(unsigned int section_bytes, bool with_fuzz, int min_blocks = XR_SPAN_MINBLOCKS) {
+    const size_t budget = (size_t)216 * 1024 / (size_t)min_blocks - 1024;  // 228 KB per SM, 1 KB per CTA reserved, some slack
     const size_t sec = (section_bytes + 15u) & ~15u;
     const size_t fz = with_fuzz ? (size_t)kSpanFuzzCap * kBlockThreads * 4 : 0;
     if (budget < sec + fz + (size_t)8 * kBlockThreads * 8) return 0;
@@ -72,8 +73,8 @@ static int span_list_cap(unsigned int section_bytes, bool with_fuzz) {
     return (int)(cap < (size_t)kSpanCapMax ? cap : (size_t)kSpanCapMax);
 }
 
-static size_t span_smem_bytes(unsigned int section_bytes, bool with_fuzz) {
-    const int cap = span_list_cap(section_bytes, with_fuzz);
+static size_t span_smem_bytes(unsigned int section_bytes, bool with_fuzz, int min_blocks = XR_SPAN_MINBLOCKS) {
+    const int cap = span_list_cap(section_bytes, with_fuzz, min_blocks);
     if (cap <= 0) return (size_t)1 << 30;  // does not fit: the caller keeps to the marching kernels
     return (size_t)((section_bytes + 15u) & ~15u) + (size_t)cap * kBlockThreads * 8 + (with_fuzz ? (size_t)kSpanFuzzCap * kBlockThreads * 4 : 0);
 }
@@ -550,8 +551,10 @@ __device__ __forceinline__ double span_combine(const SpanChild* __restrict__ ch,
 // does not carry it).  Whatever neither pass can vouch for goes to the marching kernels.
 // WALK = false (fast pass of a launch with screen-space bins): the grid walk is not compiled in -- it costs the binned hot
 // loop 3-7 % in registers -- and the few tiles whose bin overflowed are left to the settle pass, which always has it.
-template <int INTEG, bool COUNT, bool SETTLE, bool WALK>
-__global__ void __launch_bounds__(kBlockThreads, XR_SPAN_MINBLOCKS) render_span_kernel(const RenderParams P, const unsigned char* __restrict__ nfine,
+// MINB = CTAs per SM the registers are budgeted for: 4 (128 registers), or 5 (96) for the binned fast pass when the scene's
+// section leaves room for lists of kSpanCapDense entries in a fifth of the shared memory (+10 % on configs 2 and 5).
+template <int INTEG, bool COUNT, bool SETTLE, bool WALK, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) render_span_kernel(const RenderParams P, const unsigned char* __restrict__ nfine,
                                                                        const SpanArgs SA) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -1228,13 +1231,15 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
     const size_t tiles = (size_t)P.n_views * P.tiles_i * P.tiles_j;
     if (tiles == 0) return cudaSuccess;
     if (tiles * 4 > 0xffffffffull) return cudaErrorInvalidValue;
-    const size_t smem_fast = span_smem_bytes(section_bytes, false), smem_settle = span_smem_bytes(section_bytes, true);
+    const bool dense = d_bins && bin_cap > 0 && n_instances > 0 && span_list_cap(section_bytes, false, XR_SPAN_MINBLOCKS + 1) >= kSpanCapDense;
+    const int fast_blocks = dense ? XR_SPAN_MINBLOCKS + 1 : XR_SPAN_MINBLOCKS;
+    const size_t smem_fast = span_smem_bytes(section_bytes, false, fast_blocks), smem_settle = span_smem_bytes(section_bytes, true);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // work lists: d_tile_list[0 .. items) = hand-over to the marching kernels, [items .. 2 items) = settle pass
     SpanArgs SA = {d_section, section_bytes, d_tile_list, d_tile_count, d_tile_list + tiles * 4, (unsigned int)(tiles * 4),
-                   span_list_cap(section_bytes, false), nullptr, nullptr, 0u};
+                   span_list_cap(section_bytes, false, fast_blocks), nullptr, nullptr, 0u};
     if (d_bins && bin_cap > 0 && n_instances > 0) {
         cudaError_t eb = cudaMemsetAsync(d_bins, 0, tiles * sizeof(unsigned int), stream);
         if (eb != cudaSuccess) return eb;
@@ -1253,8 +1258,10 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
     const unsigned int grid_settle = (unsigned int)(tiles < (size_t)sms ? tiles : (size_t)sms);
 #define XR_SGO(I, C)                                                                                                        \
     do {                                                                                                                    \
-        auto fast = SA.bin_counts ? render_span_kernel<I, C, false, false> : render_span_kernel<I, C, false, true>;         \
-        auto settle = render_span_kernel<I, C, true, true>;                                                                 \
+        auto fast = dense ? render_span_kernel<I, C, false, false, XR_SPAN_MINBLOCKS + 1>                                   \
+                          : (SA.bin_counts ? render_span_kernel<I, C, false, false, XR_SPAN_MINBLOCKS>                      \
+                                           : render_span_kernel<I, C, false, true, XR_SPAN_MINBLOCKS>);                     \
+        auto settle = render_span_kernel<I, C, true, true, XR_SPAN_MINBLOCKS>;                                              \
         cudaError_t e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);            \
         if (e == cudaSuccess) e = cudaFuncSetAttribute(settle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_settle); \
         if (e != cudaSuccess) return e;                                                                                     \
