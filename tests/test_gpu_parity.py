@@ -234,6 +234,38 @@ def test_big_collections_use_cell_lists(X, O, greedy, kernel_path):
     assert out["fp32"][1]["primitive_tests"] < 0.05 * out["fp32"][1]["evaluated_samples"] * len(objs)
 
 
+@pytest.mark.parametrize("n", [62, 63, 64, 65])
+@pytest.mark.parametrize("wrap", ["flat", "tess"])
+def test_collection_sizes_around_the_mask_width(X, O, n, wrap, kernel_path):
+    """63 / 64 / 65 children: the marching kernels' 64-bit child masks keep bit 63 for "empty cell, skip distance", so a
+    collection of exactly 64 must already take the cell lists (it took the masks in r1 and child 63 vanished wherever it
+    was listed: found by soaking tests/test_gpu_fuzz.py over 1200 more seeds); the interval renderer takes up to 64."""
+    rng = np.random.default_rng(6400 + n)
+    objs = []
+    for k in range(n):
+        c = rng.uniform(-0.45, 0.45, 3)
+        kind = k % 4
+        rho = float(rng.choice([1.0, 0.6, -0.4, 0.3]))
+        if kind == 0:
+            objs.append({"type": "sphere", "center": list(c), "radius": float(rng.uniform(0.04, 0.12)), "rho": rho})
+        elif kind == 1:
+            objs.append({"type": "box", "center": list(c), "sides": list(rng.uniform(0.05, 0.25, 3)), "rho": rho})
+        elif kind == 2:
+            objs.append({"type": "cylinder", "p0": list(c), "p1": list(c + rng.uniform(-0.3, 0.3, 3)), "radius": float(rng.uniform(0.02, 0.08)), "rho": rho})
+        else:
+            m = np.eye(3) * rng.uniform(0.08, 0.2, 3) + rng.uniform(-0.04, 0.04, (3, 3))
+            objs.append({"type": "parallelepiped", "origin": list(c), "v0": list(m[0]), "v1": list(m[1]), "v2": list(m[2]), "rho": rho})
+    objs[-1] = {"type": "sphere", "center": [0.05, -0.1, 0.1], "radius": 0.3, "rho": 0.45}  # the LAST child is the big one
+    if wrap == "flat":
+        obj = {"type": "object_collection", "objects": objs, "greedy_dens_eval": bool(n % 2)}
+    else:
+        uc = {"objects": {"objects": objs}, "xmin": -0.5, "xmax": 0.5, "ymin": -0.5, "ymax": 0.5, "zmin": -0.5, "zmax": 0.5}
+        obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.9, "xmax": 0.9, "ymin": -0.8, "ymax": 0.8, "zmin": -0.7, "zmax": 0.7}
+    for integ in ("hierarchical", "simple"):
+        out, nref, _ = gpu_vs_oracle(X, O, obj, res=32, ds=0.01, integ=integ, views=((100.0, 80.0), (10.0, 95.0)))
+        assert_parity(out, nref)
+
+
 def test_big_unit_cell_collection(X, O):
     """A tessellated unit cell with > 63 struts (cell lists under the periodic fold + skip distances)."""
     uc_objs = _foam(2, 0.02)

@@ -1,3 +1,2 @@
-python tools/span_time.py lattice pillar cube box_w_pped balls 2>&1 | tail -5
-python tools/span_reasons.py 2>&1 | grep -v "marched_tiles     0"
-timeout 900 python -m pytest tests/test_gpu_span.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py -q -m gpu -x 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "mask_width or big" 2>&1 | tail -15
+timeout 1500 python tools/fuzz_soak.py 150 1600 2>&1 | tail -30

@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) render_span_kernel(const 
                                                                        const SpanArgs SA) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+    if (SETTLE && blockIdx.x * (kBlockThreads / 32) >= SA.tile_count[1]) return;  // (usually a handful of warp tiles: most CTAs leave here)
     {
         uint4* dst = reinterpret_cast<uint4*>(smem);
         const uint4* src = reinterpret_cast<const uint4*>(SA.section);

@@ -1005,7 +1005,7 @@ static double g_grid_feat_scale = 0.25;  // cell size in units of the smallest c
 static bool build_grid(Builder& B, const Node& coll, const Box3* region, uint32_t& f32_idx, uint32_t& grid_idx) {
     size_t n = coll.kids.size();
     // a unit-cell collection is worth a grid even for one child: the grid also drives empty-space skipping
-    if ((int)n < (region ? 1 : g_grid_min_children) || n > 64) return false;
+    if ((int)n < (region ? 1 : g_grid_min_children) || n > 63) return false;  // (bit 63 of a mask marks an empty cell)
     Box3 reg;
     if (region) reg = *region;
     else
