@@ -312,3 +312,93 @@ def test_go_host_probe_from_c(X, host_replay):
     # the analytic-scene call sequence integration/go_host.patch adds to the host (compile JSON, render, free)
     r = subprocess.run([host_replay, lib, "scene"], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok scene", r.stderr
+
+
+def _hier_case(X, O, vol, views, res, ds, ff=0.0, dm=1.0):
+    """Hierarchical integrator over a voxel grid, fp32 mode through the dedicated kernel, against the oracle: image, the
+    reference-equivalent sample count (coarse + refined fine samples) and that the dedicated kernel really ran."""
+    cams = X.cameras_from_angles(views, R, FOV)
+    osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)}, flat_field=ff, density_multiplier=dm)
+    ref, nref = [], 0
+    for az, pol in views:
+        im, k = osc.render_view(*O.camera_from_angles(az, pol, R), res, FOV, R, ds, "hierarchical")
+        ref.append(im)
+        nref += k
+    ref = np.stack(ref)
+    img, st = X.render_volume(vol, cams, res, integration="hierarchical", precision="fp32", ds=ds, flat_field=ff, density_multiplier=dm,
+                              return_stats=True)
+    assert np.abs(img.astype(np.float64) - ref).max() <= TOL_FP32
+    assert st["ref_samples"] == nref
+    return img, st, ref
+
+
+def test_hierarchical_volume_kernel(X, O, monkeypatch):
+    """integrate_hierarchical (main.go:159-199) over VoxelGrid.Density: blobs in empty space (the ray enters and leaves
+    the support several times: every such coarse interval is refined), a one-voxel plate, isolated voxels, -0.0, values on
+    the cube's border, seen along the axes (whole pixel rows inside voxel-face planes: every sample is settled in fp64)
+    and obliquely; non-zero flat field and a density multiplier."""
+    rng = np.random.default_rng(33)
+    nz, nx, ny = 40, 48, 56
+    vol = np.zeros((nz, nx, ny), dtype=np.float32)
+    k, i, j = np.meshgrid(np.arange(nz), np.arange(nx), np.arange(ny), indexing="ij")
+    for _ in range(5):
+        c = rng.uniform(0.2, 0.8, 3) * np.array([nz, nx, ny])
+        r = rng.uniform(3.0, 8.0)
+        m = (k - c[0]) ** 2 + (i - c[1]) ** 2 + (j - c[2]) ** 2 < r * r
+        vol[m] = rng.random(int(m.sum()), dtype=np.float32) * 0.8 + 0.1
+    vol[20, :, 10:30] = 0.5
+    for _ in range(10):
+        vol[rng.integers(nz), rng.integers(nx), rng.integers(ny)] = rng.random()
+    vol[0, 0, 0] = 0.9
+    vol[-1, -1, 5:20] = 0.4
+    vol[5:9, 30:40, 5:9] = -0.0
+    views = [(0.0, 90.0), (90.0, 90.0), (33.0, 90.0), (118.0, 61.0), (45.0, 35.0)]
+    ds = 2.0 / 56 / 3.0
+    for res in (32, 33):
+        img, st, _ = _hier_case(X, O, vol, views, res, ds, ff=0.03, dm=1.3)
+        assert img.min() < 0.9
+        # the dedicated kernel: nearly every sample by the closed-form cell sums, the fp64 routine only for the refined
+        # intervals and for samples within 1e-5 voxel of a cell face
+        assert st["fp64_fallbacks"] < 0.4 * st["evaluated_samples"], st
+    monkeypatch.setenv("XRAY_VOLUME_GENERIC", "1")
+    _, st0, _ = _hier_case(X, O, vol, views[2:], 32, ds, ff=0.03, dm=1.3)
+    monkeypatch.delenv("XRAY_VOLUME_GENERIC")
+    _, st1, _ = _hier_case(X, O, vol, views[2:], 32, ds, ff=0.03, dm=1.3)
+    assert st1["ref_samples"] == st0["ref_samples"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_hierarchical_volume_kernel_random(X, O, seed):
+    """Random shapes (also a single layer / column), random sparsity, half of them with mixed-sign values (the interpolant
+    crosses zero inside cells: zero-ness is then decided per sample), dm of either sign or zero, random views."""
+    rng = np.random.default_rng(4400 + seed)
+    shape = tuple(int(v) for v in rng.choice([1, 2, 3, 7, 16, 24, 33], 3))
+    vol = rng.random(shape, dtype=np.float32)
+    if seed % 2:
+        vol -= np.float32(0.5)
+    vol[rng.random(shape) < rng.choice([0.0, 0.5, 0.9, 0.99])] = 0.0
+    if seed % 3 == 0:  # whole-number values: exact cancellations of the lerp are then possible
+        vol = np.round(vol * 4).astype(np.float32)
+    views = [(float(rng.choice([0.0, 90.0, 45.0, rng.uniform(0, 360)])), float(rng.choice([90.0, rng.uniform(30, 150)]))) for _ in range(2)]
+    ds = float(rng.choice([0.05, 0.02, 0.011]))
+    dm = float(rng.choice([1.0, 0.6, -0.7, 0.0]))
+    _hier_case(X, O, vol, views, int(rng.choice([16, 21, 32])), ds, ff=float(rng.choice([0.0, 0.1])), dm=dm)
+
+
+def test_voxel_grid_object_file_takes_the_volume_kernel(X, O):
+    """A scene that is nothing but one fp32 voxel grid (what a voxel_grid object file compiles to) is rendered by the dedicated
+    voxel kernel from the scene entry points too: same images and counters as XRayRenderVolumeExCUDA, both integrators."""
+    rng = np.random.default_rng(5)
+    vol = (rng.random((18, 22, 26)) * (rng.random((18, 22, 26)) < 0.4)).astype(np.float32)
+    views = [(20.0, 80.0), (200.0, 100.0)]
+    cams = X.cameras_from_angles(views, R, FOV)
+    sc = X.Scene({"type": "voxel_grid", "_array": vol})
+    ds = 2.0 / 26 / 4.0
+    for integ in ("simple", "hierarchical"):
+        a, sa = X.render_scene(sc, cams, 40, integration=integ, ds=ds, return_stats=True)
+        b, sb = X.render_volume(vol, cams, 40, integration=integ, precision="fp32", ds=ds, return_stats=True)
+        assert np.array_equal(a, b)
+        assert (sa["ref_samples"], sa["evaluated_samples"], sa["fp64_fallbacks"]) == (sb["ref_samples"], sb["evaluated_samples"], sb["fp64_fallbacks"])
+        osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)})
+        ref = np.stack([osc.render_view(*O.camera_from_angles(az, pol, R), 40, FOV, R, ds, integ)[0] for az, pol in views])
+        assert np.abs(a.astype(np.float64) - ref).max() <= TOL_FP32

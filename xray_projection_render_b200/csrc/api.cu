@@ -41,7 +41,8 @@ cudaError_t launch_render_span(const RenderParams& P, int integrator, bool count
                                unsigned int bin_cap, unsigned int n_instances, cudaStream_t stream);
 size_t span_kernel_smem_bytes(unsigned int section_bytes);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                     int warp_shape, const unsigned char* occ, cudaStream_t stream);
+                                     int warp_shape, const unsigned char* occ, int integrator, const unsigned char* d_nfine,
+                                     cudaStream_t stream);
 size_t volume_brick_count(int nx, int ny, int nz);
 cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
                                    const unsigned char** result, unsigned long long surf, cudaStream_t stream);
@@ -826,8 +827,9 @@ static int run_job(Job& J) {
     auto launch_march = [&](cudaStream_t stream) -> cudaError_t {  // (shadows the job's stream on purpose)
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
-                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, (int)(P.cams - C->d_cams), P.n_views), vol_occ, stream);
-        if (J.fast_volume)
+                                            h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, (int)(P.cams - C->d_cams), P.n_views), vol_occ,
+                                            J.opts.integration == XRAY_INTEGRATE_HIERARCHICAL ? 1 : 0, C->d_nfine, stream);
+        if (J.fast_volume && J.opts.integration == XRAY_INTEGRATE_SIMPLE)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
         if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && single_async && P.prog_in_smem && fast_kernel_smem_bytes(P) <= 200 * 1024)
@@ -1040,6 +1042,8 @@ static bool fp32_position_bound_ok(const Header* h, const XRayCameraParams64* ca
     return true;
 }
 
+static bool volume_fast_path_ok(const XRayRenderOpts& o, int dtype);
+
 static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n, int res, const XRayRenderOpts* opts_in,
                          void* out, bool out_on_device, const void* borrowed_vox, bool fast_volume) {
     if (!scene || !cams || !out) return fail(1, "null pointer argument");
@@ -1076,6 +1080,11 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
     // |dx| <= u32 * (3*|t|max + |pc| + |x|).  A distant camera or a wide field of view puts pc = o + d*R far
     // from the origin; such calls are promoted to the fp64 kernels (slower, always exact) instead of risking a
     // misclassified sample.
+    // A scene that is nothing but one fp32 voxel grid (a voxel_grid object file, no deformation) is what the volume entry
+    // points build for themselves: it takes the dedicated voxel kernel from the scene entry points as well.
+    if (!fast_volume && scene->root.type == N_VOXEL && scene->deforms.empty() && h->n_voxel_slots == 1 && !borrowed_vox &&
+        scene->vox[0].data && scene->vox[0].dtype == XRAY_VOXEL_F32)
+        fast_volume = volume_fast_path_ok(opts, XRAY_VOXEL_F32);
     if (opts.precision == XRAY_PRECISION_FP32 && !fp32_position_bound_ok(h, cams, n, res)) {
         opts.precision = XRAY_PRECISION_FP64;
         fast_volume = false;
@@ -1345,7 +1354,7 @@ static int make_volume_scene(int nx, int ny, int nz, XRayScene** out) {
 
 static bool volume_fast_path_ok(const XRayRenderOpts& o, int dtype) {
     if (getenv("XRAY_VOLUME_GENERIC")) return false;
-    return dtype == XRAY_VOXEL_F32 && o.precision == XRAY_PRECISION_FP32 && o.integration == XRAY_INTEGRATE_SIMPLE;
+    return dtype == XRAY_VOXEL_F32 && o.precision == XRAY_PRECISION_FP32;  // both integrators (hierarchical: the texture kernel only)
 }
 
 extern "C" {

@@ -221,11 +221,19 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int laye
 
 // WI x WJ = the pixel footprint of one warp (i = camera x, j = camera y; j is the fast output index).  The best
 // shape is the one whose lanes share texture layers (z): the launcher picks it from the camera orientation.
-template <int WI, int WJ>
+//
+// INTEG = 1: integrate_hierarchical (main.go:159-199).  Its coarse samples are the lattice positions s_tab[k + 1], k in
+// [0, n): the same closed-form sum, over the lattice shifted by one.  On top of it every coarse interval whose sample
+// flips (rho == 0) != (prev_rho == 0) is refined: T += ds_fine * (sum of its fine samples + rho) instead of DS * rho.  Zero-ness
+// is exact by construction: a sample safely inside a cell whose 8 corners are all 0 is 0; safely inside a cell whose
+// corners are not all 0 and share a sign it is not 0; every other sample (closer than tolw to a cell face in fp32, or in
+// a mixed-sign cell with a small value) is evaluated with the reference's own fp64 expression.  The refined intervals (a
+// handful per ray: where it enters or leaves the support of the volume) are evaluated sample by sample in fp64.
+template <int WI, int WJ, int INTEG>
 __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const RenderParams P, cudaTextureObject_t tex,
                                                                          const float* __restrict__ vol, int nx, int ny, int nz,
                                                                          float tol, const unsigned char* __restrict__ occ, int bnx,
-                                                                         int bny) {
+                                                                         int bny, const unsigned char* __restrict__ nfine) {
     static_assert(WI * WJ == 32, "one warp");
     int view, i, j;
     {  // block = 2 x 2 warps
@@ -249,9 +257,10 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     const bool hit = valid && clip_ray(ray, lo_o, hi_o, s_in, s_out);
     const bool hit_inner = hit && clip_ray(ray, lo_i, hi_i, q_in, q_out);
     int k0, k1, m0 = 0, m1 = 0;
-    step_range(P, hit, s_in, s_out, 0, k0, k1);
+    constexpr int OFF = INTEG == 1 ? 1 : 0;  // sample k sits at s_tab[k + OFF]
+    step_range(P, hit, s_in, s_out, OFF, k0, k1);
     if (hit_inner) {
-        double a = ceil((q_in - P.smin) / P.ds) + 1.0, b = floor((q_out - P.smin) / P.ds) - 1.0;
+        double a = ceil((q_in - P.smin) / P.ds) + 1.0 - (double)OFF, b = floor((q_out - P.smin) / P.ds) - 1.0 - (double)OFF;
         a = fmin(fmax(a, (double)k0), (double)k1);
         b = fmin(fmax(b + 1.0, a), (double)k1);
         m0 = (int)a;
@@ -271,28 +280,60 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     }
     unsigned int n_eval = 0, n_fallback = 0;
     double tot = 0.0;
+    VoxelDev vd;
+    vd.data = vol;
+    vd.nx = nx;
+    vd.ny = ny;
+    vd.nz = nz;
+    vd.dtype = 0;
+    // the reference's density at lattice parameter s (main.go:147-149 position, objects.go:789-855)
+    auto exact_at = [&](double s) -> double {
+        const double x = dadd(ray.o[0], dmul(ray.d[0], s));
+        const double y = dadd(ray.o[1], dmul(ray.d[1], s));
+        const double z = dadd(ray.o[2], dmul(ray.d[2], s));
+        return voxel_exact(vd, x, y, z);
+    };
+    // hierarchical integrator: zero-ness of the last coarse sample, the refinements' sum, their fine-sample count
+    bool prev_z = true;  // prev_rho := 0.0 (main.go:179)
+    double corr = 0.0;
+    unsigned int n_fine = 0;
+    // coarse sample k (interval [s_tab[k], s_tab[k + 1]]) is zero (z) or not: refine the interval if that flips
+    auto see = [&](int k, bool z) {
+        if (z != prev_z) {
+            const int nf = (int)__ldg(nfine + k);
+            double s = P.s_tab[k], fsum = 0.0;
+            for (int q = 0; q < nf; ++q) {
+                s = dadd(s, P.ds_fine);  // main.go:183,189: left += ds
+                fsum += exact_at(s);
+            }
+            const double rk = z ? 0.0 : exact_at(P.s_tab[k + 1]);
+            corr += P.ds_fine * (fsum + rk) - P.ds * rk;
+            n_fine += (unsigned int)nf;
+            n_fallback += (unsigned int)nf + 1u;
+        }
+        prev_z = z;
+    };
+    const bool dm_zero = P.dm == 0.0;  // (rho * 0 == 0 everywhere: nothing ever flips)
 
     // (1) guard-band samples at the entry and exit faces: exact fp64 (a handful per ray)
-    {
-        VoxelDev vd;
-        vd.data = vol;
-        vd.nx = nx;
-        vd.ny = ny;
-        vd.nz = nz;
-        vd.dtype = 0;
+    if (INTEG == 0) {
         const int nb_in = m0 - k0, nb = nb_in + (k1 - m1);
         const int wmax = __reduce_max_sync(FULL_MASK, hit ? nb : 0);
         for (int r = 0; r < wmax; ++r) {
             if (hit && r < nb) {
                 const int k = r < nb_in ? k0 + r : m1 + (r - nb_in);
-                const double s = P.s_tab[k];
-                const double x = dadd(ray.o[0], dmul(ray.d[0], s));
-                const double y = dadd(ray.o[1], dmul(ray.d[1], s));
-                const double z = dadd(ray.o[2], dmul(ray.d[2], s));
-                tot += voxel_exact(vd, x, y, z);
+                tot += exact_at(P.s_tab[k]);
                 ++n_eval;
                 ++n_fallback;
             }
+        }
+    } else if (hit) {  // in lattice order: the entry face now, the exit face after the interior
+        for (int k = k0; k < m0; ++k) {
+            const double r = exact_at(P.s_tab[k + OFF]);
+            tot += r;
+            see(k, dm_zero || r == 0.0);
+            ++n_eval;
+            ++n_fallback;
         }
     }
 
@@ -313,8 +354,9 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     const float dwx = dux * P.ds_f, dwy = duy * P.ds_f, dwz = duz * P.ds_f;
     const float dxy = dwx * dwy, dxz = dwx * dwz, dyz = dwy * dwz, dxyz = dwx * dwy * dwz;
     // sample parameter t_k = s_k - R without the table: t0 + (k - kref)*ds, ds split hi + lo (half an ulp, like the table)
-    const int kref = P.n_steps >> 1;
-    const float t0 = P.t_tab[kref];
+    const int kref = (P.n_steps >> 1) - OFF;  // (k - kref = lattice index - n_steps / 2)
+    const float t0 = P.t_tab[P.n_steps >> 1];
+    const float tolw = 5.0e-7f * (float)max(nx, max(ny, nz)) + 2.0e-6f;  // fp32 error of an index-space position, with margin
     const float ds_lo = (float)(P.ds - (double)P.ds_f);
     const float ivx = fabsf(dwx) > 1e-12f ? 1.0f / dwx : 0.0f, hvx = fabsf(dwx) > 1e-12f ? 0.5f / fabsf(dwx) : 1e30f;
     const float ivy = fabsf(dwy) > 1e-12f ? 1.0f / dwy : 0.0f, hvy = fabsf(dwy) > 1e-12f ? 0.5f / fabsf(dwy) : 1e30f;
@@ -342,6 +384,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
                                           (__float_as_uint(a.w) | __float_as_uint(b.x) | __float_as_uint(b.y)) |
                                           (__float_as_uint(b.z) | __float_as_uint(b.w));
             float part = 0.0f;
+            float hc0 = 0.0f, hc1 = 0.0f, hc2 = 0.0f, hc3 = 0.0f;  // (INTEG = 1) the cell's cubic along the ray
             if ((any_bits << 1) == 0u) {
                 // all eight corners are +-0: this cell adds nothing.  If the whole brick is empty, run to the edge of
                 // the empty region around it: cells [8(b-(d-1)), 8(b+d)) per axis, d = Chebyshev distance in bricks.
@@ -383,6 +426,47 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
             const float S2 = S1 * fmaf(2.0f, nf, -1.0f) * 0.333333343f;
             const float S3 = S1 * S1;
             part = fmaf(c3, S3, fmaf(c2, S2, fmaf(c1, S1, c0 * nf)));
+            if (INTEG == 1) { hc0 = c0; hc1 = c1; hc2 = c2; hc3 = c3; }
+            }
+            if (INTEG == 1) {
+                // zero-ness of the n coarse samples of this cell, in lattice order
+                const bool zcell = (any_bits << 1) == 0u;
+                // sample q of the run sits at w + q dw: closer than tolw to a face of its cell?
+                auto near = [&](int q) -> bool {
+                    const float qf = (float)q;
+                    float ax = fmaf(qf, dwx, wx), ay = fmaf(qf, dwy, wy), az = fmaf(qf, dwz, wz);
+                    ax = fabsf(ax - rintf(ax));
+                    ay = fabsf(ay - rintf(ay));
+                    az = fabsf(az - rintf(az));
+                    return fminf(ax, fminf(ay, az)) < tolw;
+                };
+                auto exact_zero = [&](int kk) -> bool { return dm_zero || dmul(exact_at(P.s_tab[kk + OFF]), P.dm) == 0.0; };
+                const bool neg = fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) < 0.0f;
+                const bool pos = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))) > 0.0f;
+                if (dm_zero) {
+                    // nothing flips
+                } else if (neg && pos) {  // the interpolant may cross zero inside the cell: sample by sample
+                    const float vmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                             fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+                    for (int q = 0; q < n; ++q) {
+                        const float qf = (float)q;
+                        const float val = fmaf(qf, fmaf(qf, fmaf(qf, hc3, hc2), hc1), hc0);
+                        const bool sure = !near(q) && fabsf(val) > 1.0e-3f * vmax;
+                        see(k + q, sure ? false : exact_zero(k + q));
+                    }
+                } else {
+                    int lead = 0;
+                    while (lead < n && near(lead)) {
+                        see(k + lead, exact_zero(k + lead));
+                        ++lead;
+                    }
+                    if (lead < n) {
+                        int trail = n;
+                        while (trail > lead + 1 && near(trail - 1)) --trail;  // [trail, n): doubtful again
+                        see(k + lead, zcell);  // [lead, trail): surely all alike, so only the first can flip
+                        for (int q = trail; q < n; ++q) see(k + q, exact_zero(k + q));
+                    }
+                }
             }
             k += n;
             const float y_ = part - cmp;
@@ -393,7 +477,17 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     }
     if (hit) n_eval += (unsigned int)(m1 - m0) - n_skip;
     tot += (double)acc - (double)cmp;
-    const double T = P.flat_field + P.ds * (tot * P.dm);
+    if (INTEG == 1 && hit) {
+        for (int k = m1; k < k1; ++k) {  // the exit face
+            const double r = exact_at(P.s_tab[k + OFF]);
+            tot += r;
+            see(k, dm_zero || r == 0.0);
+            ++n_eval;
+            ++n_fallback;
+        }
+        if (k1 < P.n_steps) see(k1, true);  // the first sample beyond the cube is 0 (objects.go:795)
+    }
+    const double T = P.flat_field + (P.ds * tot + corr) * P.dm;
     if (WJ % 4 == 0) {
         store_pixel(P, view, i, j, valid, exp(-T));
     } else if (valid) {  // narrow warp footprints: lanes 4q..4q+3 are not 4 consecutive j
@@ -401,7 +495,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
         if (P.out_f64) reinterpret_cast<double*>(P.out)[idx] = exp(-T);
         else reinterpret_cast<float*>(P.out)[idx] = (float)exp(-T);
     }
-    add_stats(P, valid ? (unsigned long long)P.n_steps : 0ull, n_eval, n_fallback, n_eval, valid ? 1ull : 0ull);
+    add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, n_eval, valid ? 1ull : 0ull);
 }
 
 static const float kVolumeGuardTol = 4.0e-6f;  // fp32 position error (1e-6, scene_compile.cpp) with margin
@@ -415,26 +509,31 @@ cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz
 
 template <int WI, int WJ>
 static cudaError_t launch_tex_shape(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                    const unsigned char* occ, cudaStream_t stream) {
+                                    const unsigned char* occ, int integrator, const unsigned char* d_nfine, cudaStream_t stream) {
     const size_t ti = (size_t)(P.res + 2 * WI - 1) / (2 * WI), tj = (size_t)(P.res + 2 * WJ - 1) / (2 * WJ);
     const size_t grid = (size_t)P.n_views * ti * tj;
     if (grid == 0) return cudaSuccess;
     if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
-    render_volume_tex_kernel<WI, WJ><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(
-        P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz, kVolumeGuardTol, occ, (nx + kBrick - 1) / kBrick, (ny + kBrick - 1) / kBrick);
+    if (integrator == 0)
+        render_volume_tex_kernel<WI, WJ, 0><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(
+            P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz, kVolumeGuardTol, occ, (nx + kBrick - 1) / kBrick, (ny + kBrick - 1) / kBrick, d_nfine);
+    else
+        render_volume_tex_kernel<WI, WJ, 1><<<(unsigned int)grid, kBlockThreads, 0, stream>>>(
+            P, (cudaTextureObject_t)tex, d_vol, nx, ny, nz, kVolumeGuardTol, occ, (nx + kBrick - 1) / kBrick, (ny + kBrick - 1) / kBrick, d_nfine);
     return cudaGetLastError();
 }
 
 // warp_shape: 0 = 4 x 8 pixels (i x j), 1 = 32 x 1, 2 = 1 x 32, 3 = 16 x 2, 4 = 2 x 16, 5 = 8 x 4
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
-                                     int warp_shape, const unsigned char* occ, cudaStream_t stream) {
+                                     int warp_shape, const unsigned char* occ, int integrator, const unsigned char* d_nfine,
+                                     cudaStream_t stream) {
     switch (warp_shape) {
-        case 1: return launch_tex_shape<32, 1>(tex, d_vol, nx, ny, nz, P, occ, stream);
-        case 2: return launch_tex_shape<1, 32>(tex, d_vol, nx, ny, nz, P, occ, stream);
-        case 3: return launch_tex_shape<16, 2>(tex, d_vol, nx, ny, nz, P, occ, stream);
-        case 4: return launch_tex_shape<2, 16>(tex, d_vol, nx, ny, nz, P, occ, stream);
-        case 5: return launch_tex_shape<8, 4>(tex, d_vol, nx, ny, nz, P, occ, stream);
-        default: return launch_tex_shape<4, 8>(tex, d_vol, nx, ny, nz, P, occ, stream);
+        case 1: return launch_tex_shape<32, 1>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
+        case 2: return launch_tex_shape<1, 32>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
+        case 3: return launch_tex_shape<16, 2>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
+        case 4: return launch_tex_shape<2, 16>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
+        case 5: return launch_tex_shape<8, 4>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
+        default: return launch_tex_shape<4, 8>(tex, d_vol, nx, ny, nz, P, occ, integrator, d_nfine, stream);
     }
 }
 
