@@ -327,7 +327,8 @@ def _hier_case(X, O, vol, views, res, ds, ff=0.0, dm=1.0):
     ref = np.stack(ref)
     img, st = X.render_volume(vol, cams, res, integration="hierarchical", precision="fp32", ds=ds, flat_field=ff, density_multiplier=dm,
                               return_stats=True)
-    assert np.abs(img.astype(np.float64) - ref).max() <= TOL_FP32
+    # (a negative multiplier makes "transmissions" of several hundred: the 1e-4 gate is meant for values in [0, 1])
+    assert (np.abs(img.astype(np.float64) - ref) <= TOL_FP32 * np.maximum(1.0, ref)).all()
     assert st["ref_samples"] == nref
     return img, st, ref
 

@@ -16,5 +16,7 @@ for seed in range(first, last):
         T.test_hierarchical_volume_kernel_random(X, O, seed)
     except AssertionError as e:
         bad += 1
-        print("FAIL", seed, str(e)[:200].replace("\n", " "), flush=True)
+        import traceback
+        tb = traceback.extract_tb(e.__traceback__)[-1]
+        print("FAIL", seed, tb.lineno, tb.line, str(e)[:200].replace("\n", " "), flush=True)
 print("done", first, last, "failures", bad)
