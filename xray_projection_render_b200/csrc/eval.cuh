@@ -363,7 +363,24 @@ struct Fast {
         float v00 = fmaf(wz, v001 - v000, v000), v01 = fmaf(wz, v011 - v010, v010);
         float v10 = fmaf(wz, v101 - v100, v100), v11 = fmaf(wz, v111 - v110, v110);
         float v0 = fmaf(wy, v01 - v00, v00), v1 = fmaf(wy, v11 - v10, v10);
-        return fmaf(wx, v1 - v0, v0);
+        const float val = fmaf(wx, v1 - v0, v0);
+        // The VALUE is continuous, so fp32 is good to ~1e-6 everywhere inside the cube.  Whether it is exactly ZERO is not
+        // (integrate_hierarchical refines where (rho == 0) flips, main.go:180): safely inside a cell the reference's lerp is 0
+        // iff all eight corners are (same-sign corners cannot cancel); within the position error of a cell face the sample
+        // may belong to the neighbouring cell, and in a mixed-sign cell the interpolant may cross zero: fp64 decides those.
+        {
+            const float tix = fmaf(tol, 0.5f * (float)(v.nx - 1), 4.0e-7f * (float)v.nx);
+            const float tiy = fmaf(tol, 0.5f * (float)(v.ny - 1), 4.0e-7f * (float)v.ny);
+            const float tiz = fmaf(tol, 0.5f * (float)(v.nz - 1), 4.0e-7f * (float)v.nz);
+            // (an axis with a single layer has x1 == x0: its weight does not matter)
+            const bool face = (v.nx > 1 && fminf(wx, 1.0f - wx) < tix) || (v.ny > 1 && fminf(wy, 1.0f - wy) < tiy) ||
+                              (v.nz > 1 && fminf(wz, 1.0f - wz) < tiz);
+            const float lo = fminf(fminf(fminf(v000, v001), fminf(v010, v011)), fminf(fminf(v100, v101), fminf(v110, v111)));
+            const float hi = fmaxf(fmaxf(fmaxf(v000, v001), fmaxf(v010, v011)), fmaxf(fmaxf(v100, v101), fmaxf(v110, v111)));
+            const bool mixed = lo < 0.0f && hi > 0.0f;
+            near = near || face || (mixed && fabsf(val) <= 1.0e-3f * fmaxf(-lo, hi));
+        }
+        return val;
     }
 };
 
