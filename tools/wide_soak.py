@@ -21,6 +21,27 @@ for seed in range(first, last):
     rng = np.random.default_rng(555000 + seed)
     kind = rng.choice(["fuzz", "span", "one"])
     obj = T.rnd_scene(rng) if kind == "fuzz" else (S._span_scene(rng) if kind == "span" else T.rnd_one_primitive_scene(rng))
+    def sparsify(o):  # voxel children with exact zeros (and sometimes mixed signs): zero-ness matters to the hierarchical integrator
+        if isinstance(o, dict):
+            if o.get("type") == "voxel_grid" and "_array" in o:
+                arr = np.array(o["_array"], dtype=np.float64)
+                if rng.random() < 0.5:
+                    arr -= 0.25
+                arr[rng.random(arr.shape) < rng.choice([0.3, 0.7, 0.95])] = 0.0
+                o["_array"] = arr
+            for v in list(o.values()):
+                sparsify(v)
+        elif isinstance(o, list):
+            for v in o:
+                sparsify(v)
+    if os.environ.get("SOAK_NESTED"):
+        kids = [T.rnd_prim(rng, allow_gyroid=False) for _ in range(int(rng.integers(0, 3)))]
+        kids.append({"type": "voxel_grid", "_array": rng.random((int(rng.integers(1, 12)), int(rng.integers(1, 12)), int(rng.integers(1, 12)))) * 0.6})
+        if rng.random() < 0.4:
+            kids.append(T.rnd_tess(rng))
+        rng.shuffle(kids)
+        obj = {"type": "object_collection", "greedy_dens_eval": bool(rng.random() < 0.3), "objects": kids}
+    sparsify(obj)
     deform = T.rnd_deform(rng) if rng.random() < 0.5 else None
     integ = "hierarchical" if rng.random() < 0.7 else "simple"
     res = int(rng.integers(5, 71))
