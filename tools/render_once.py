@@ -21,7 +21,7 @@ if obj.startswith("voxel"):  # voxel1024 / voxel256 ...: the synthetic BASELINE 
     n = int(obj[5:])
     vol = torch.from_numpy(bench.synthetic_volume(n)).cuda()
     for _ in range(reps):
-        X.render_volume_device(vol, (n, n, n), cams, res, out, ds=2.0 / n / 5.0)
+        X.render_volume_device(vol, (n, n, n), cams, res, out, ds=2.0 / n / 5.0, integration=__import__('os').environ.get('INTEG', 'simple'))
 else:
     sc = X.Scene(str(SC / obj), str(SC / deform) if deform else None)
     for _ in range(reps):

@@ -230,7 +230,7 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, int laye
 // a mixed-sign cell with a small value) is evaluated with the reference's own fp64 expression.  The refined intervals (a
 // handful per ray: where it enters or leaves the support of the volume) are evaluated sample by sample in fp64.
 template <int WI, int WJ, int INTEG>
-__global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const RenderParams P, cudaTextureObject_t tex,
+__global__ void __launch_bounds__(kBlockThreads, INTEG == 1 ? 6 : 8) render_volume_tex_kernel(const RenderParams P, cudaTextureObject_t tex,
                                                                          const float* __restrict__ vol, int nx, int ny, int nz,
                                                                          float tol, const unsigned char* __restrict__ occ, int bnx,
                                                                          int bny, const unsigned char* __restrict__ nfine) {
@@ -298,15 +298,32 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     double corr = 0.0;
     unsigned int n_fine = 0;
     // coarse sample k (interval [s_tab[k], s_tab[k + 1]]) is zero (z) or not: refine the interval if that flips
+    // The VALUE of a sample safely inside the cube, fp32 (two texture gathers): what the refined intervals' fine samples need
+    // (their zero-ness decides nothing); inside the guard band of the cube's faces the exact routine takes over.
+    auto value_at = [&](double s) -> double {
+        if (!(hit_inner && s > q_in + 1.0e-6 && s < q_out - 1.0e-6)) return exact_at(s);
+        const float t = (float)(s - P.s_center);
+        const float ux = fmaf(dux, t, ucx), uy = fmaf(duy, t, ucy), uz = fmaf(duz, t, ucz);
+        const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+        const float wx = ux - fx, wy = uy - fy, wz = uz - fz;
+        const int z0 = max(0, min(nz - 1, (int)fz)), z1 = min(z0 + 1, nz - 1);
+        const float4 a = gather_layer(tex, z0, fy + 1.0f, fx + 1.0f);
+        const float4 b = gather_layer(tex, z1, fy + 1.0f, fx + 1.0f);
+        // .w = (y0, x0), .z = (y1, x0), .x = (y0, x1), .y = (y1, x1)
+        const float v00 = fmaf(wz, b.w - a.w, a.w), v01 = fmaf(wz, b.z - a.z, a.z);
+        const float v10 = fmaf(wz, b.x - a.x, a.x), v11 = fmaf(wz, b.y - a.y, a.y);
+        const float v0 = fmaf(wy, v01 - v00, v00), v1 = fmaf(wy, v11 - v10, v10);
+        return (double)fmaf(wx, v1 - v0, v0);
+    };
     auto see = [&](int k, bool z) {
         if (z != prev_z) {
             const int nf = (int)__ldg(nfine + k);
             double s = P.s_tab[k], fsum = 0.0;
             for (int q = 0; q < nf; ++q) {
                 s = dadd(s, P.ds_fine);  // main.go:183,189: left += ds
-                fsum += exact_at(s);
+                fsum += value_at(s);
             }
-            const double rk = z ? 0.0 : exact_at(P.s_tab[k + 1]);
+            const double rk = z ? 0.0 : value_at(P.s_tab[k + 1]);
             corr += P.ds_fine * (fsum + rk) - P.ds * rk;
             n_fine += (unsigned int)nf;
             n_fallback += (unsigned int)nf + 1u;
@@ -356,7 +373,9 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
     // sample parameter t_k = s_k - R without the table: t0 + (k - kref)*ds, ds split hi + lo (half an ulp, like the table)
     const int kref = (P.n_steps >> 1) - OFF;  // (k - kref = lattice index - n_steps / 2)
     const float t0 = P.t_tab[P.n_steps >> 1];
-    const float tolw = 5.0e-7f * (float)max(nx, max(ny, nz)) + 2.0e-6f;  // fp32 error of an index-space position, with margin
+    // fp32 error of an index-space position v = fma(du, t, vc) with |v| <= N, |du| <= N / 2, |t| < 2: half an ulp each for vc,
+    // the fma and t0, du's rounding times |t|, one ulp of t times |du|: 2.0e-7 N in all; with margin
+    const float tolw = 3.0e-7f * (float)max(nx, max(ny, nz)) + 1.0e-6f;
     const float ds_lo = (float)(P.ds - (double)P.ds_f);
     const float ivx = fabsf(dwx) > 1e-12f ? 1.0f / dwx : 0.0f, hvx = fabsf(dwx) > 1e-12f ? 0.5f / fabsf(dwx) : 1e30f;
     const float ivy = fabsf(dwy) > 1e-12f ? 1.0f / dwy : 0.0f, hvy = fabsf(dwy) > 1e-12f ? 0.5f / fabsf(dwy) : 1e30f;
@@ -385,6 +404,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
                                           (__float_as_uint(b.z) | __float_as_uint(b.w));
             float part = 0.0f;
             float hc0 = 0.0f, hc1 = 0.0f, hc2 = 0.0f, hc3 = 0.0f;  // (INTEG = 1) the cell's cubic along the ray
+            bool stretched = false;                                 // the run was stretched over an empty region
             if ((any_bits << 1) == 0u) {
                 // all eight corners are +-0: this cell adds nothing.  If the whole brick is empty, run to the edge of
                 // the empty region around it: cells [8(b-(d-1)), 8(b+d)) per axis, d = Chebyshev distance in bricks.
@@ -403,6 +423,7 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
                         if (m > n) {
                             n_skip += (unsigned int)(m - n);
                             n = m;
+                            stretched = true;
                         }
                     }
                 }
@@ -428,11 +449,17 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
             part = fmaf(c3, S3, fmaf(c2, S2, fmaf(c1, S1, c0 * nf)));
             if (INTEG == 1) { hc0 = c0; hc1 = c1; hc2 = c2; hc3 = c3; }
             }
-            if (INTEG == 1) {
-                // zero-ness of the n coarse samples of this cell, in lattice order
+            if (INTEG == 1 && !dm_zero) {
+                // Zero-ness of the n coarse samples of this run, in lattice order.  [lead, trail) = the samples that are surely
+                // all alike (zero in a cell of zeros, non-zero in a cell whose corners share a sign); the others -- closer than
+                // tolw to a face of their cell, or anywhere in a mixed-sign cell unless the value is clearly not 0 -- ask fp64.
                 const bool zcell = (any_bits << 1) == 0u;
-                // sample q of the run sits at w + q dw: closer than tolw to a face of its cell?
-                auto near = [&](int q) -> bool {
+                // some corner carries a sign bit, some does not (a cell of negatives and +0 counts as mixed: only slower)
+                const unsigned int all_bits = (__float_as_uint(a.x) & __float_as_uint(a.y) & __float_as_uint(a.z)) &
+                                              (__float_as_uint(a.w) & __float_as_uint(b.x) & __float_as_uint(b.y)) &
+                                              (__float_as_uint(b.z) & __float_as_uint(b.w));
+                const bool mixed = !zcell && (any_bits >> 31) != 0u && (all_bits >> 31) == 0u;
+                auto near = [&](int q) -> bool {  // sample q of the run sits at w + q dw (possibly several cells on)
                     const float qf = (float)q;
                     float ax = fmaf(qf, dwx, wx), ay = fmaf(qf, dwy, wy), az = fmaf(qf, dwz, wz);
                     ax = fabsf(ax - rintf(ax));
@@ -440,32 +467,48 @@ __global__ void __launch_bounds__(kBlockThreads) render_volume_tex_kernel(const 
                     az = fabsf(az - rintf(az));
                     return fminf(ax, fminf(ay, az)) < tolw;
                 };
-                auto exact_zero = [&](int kk) -> bool { return dm_zero || dmul(exact_at(P.s_tab[kk + OFF]), P.dm) == 0.0; };
-                const bool neg = fminf(fminf(fminf(a.x, a.y), fminf(a.z, a.w)), fminf(fminf(b.x, b.y), fminf(b.z, b.w))) < 0.0f;
-                const bool pos = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))) > 0.0f;
-                if (dm_zero) {
-                    // nothing flips
-                } else if (neg && pos) {  // the interpolant may cross zero inside the cell: sample by sample
-                    const float vmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
-                                             fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
-                    for (int q = 0; q < n; ++q) {
-                        const float qf = (float)q;
-                        const float val = fmaf(qf, fmaf(qf, fmaf(qf, hc3, hc2), hc1), hc0);
-                        const bool sure = !near(q) && fabsf(val) > 1.0e-3f * vmax;
-                        see(k + q, sure ? false : exact_zero(k + q));
-                    }
+                int lead = 0, trail = n;
+                if (mixed) {
+                    lead = n;  // sample by sample
                 } else {
-                    int lead = 0;
-                    while (lead < n && near(lead)) {
-                        see(k + lead, exact_zero(k + lead));
-                        ++lead;
+                    // the usual case first: neither end of the run is near a face (within one cell w stays in [0, 1]; a run
+                    // that was stretched over an empty region ends at least one step inside it)
+                    const float m_first = fminf(fminf(fminf(wx, 1.0f - wx), fminf(wy, 1.0f - wy)), fminf(wz, 1.0f - wz));
+                    float m_last = 1.0f;
+                    if (n > 1 && !stretched) {
+                        const float qf = (float)(n - 1);
+                        const float lx = fmaf(qf, dwx, wx), ly = fmaf(qf, dwy, wy), lz = fmaf(qf, dwz, wz);
+                        m_last = fminf(fminf(fminf(lx, 1.0f - lx), fminf(ly, 1.0f - ly)), fminf(lz, 1.0f - lz));
                     }
-                    if (lead < n) {
-                        int trail = n;
-                        while (trail > lead + 1 && near(trail - 1)) --trail;  // [trail, n): doubtful again
-                        see(k + lead, zcell);  // [lead, trail): surely all alike, so only the first can flip
-                        for (int q = trail; q < n; ++q) see(k + q, exact_zero(k + q));
+                    if (m_first < tolw || m_last < tolw) {
+                        while (lead < n && near(lead)) ++lead;
+                        while (trail > lead + 1 && near(trail - 1)) --trail;
                     }
+                }
+                const float vmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+                for (int q = 0; q < n;) {
+                    bool z;
+                    int adv = 1;
+                    if (q >= lead && q < trail) {
+                        z = zcell;
+                        adv = trail - q;  // only the first of them can flip
+                    } else {
+                        bool sure = false;
+                        if (mixed) {
+                            const float qf = (float)q;
+                            const float val = fmaf(qf, fmaf(qf, fmaf(qf, hc3, hc2), hc1), hc0);
+                            sure = !near(q) && fabsf(val) > 1.0e-3f * vmax;
+                        }
+                        if (sure) {
+                            z = false;
+                        } else {
+                            ++n_fallback;
+                            z = dmul(exact_at(P.s_tab[k + q + OFF]), P.dm) == 0.0;
+                        }
+                    }
+                    see(k + q, z);
+                    q += adv;
                 }
             }
             k += n;
