@@ -1,2 +1,2 @@
-timeout 600 python tools/vol_time.py 512 1024 4 2>&1 | grep "fp32"
-timeout 600 python tools/vol_time.py 1024 2048 4 2>&1 | grep "simple       fp32"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2i_bench.csv python bench.py --steps 2 --warmup 3 --no-configs --no-cpu > gpurun_out/launches_r2i_bench.log 2>&1
+tail -2 gpurun_out/launches_r2i_bench.log | cut -c1-200
