@@ -177,6 +177,25 @@ def test_rays_alongside_cell_faces(X, O, scenes, monkeypatch, bins, tilt):
     _check(X, O, str(scenes / "pillar_array.json"), views=(views[0], views[4]), res=32)
 
 
+def test_bins_that_overflow_walk_in_the_settle_pass(X, O):
+    """A fine tessellation on a coarse detector: every 8 x 16 pixel tile sees far more than 128 (period, child) instances, so
+    every bin overflows.  The binned fast pass has no grid walk compiled in: it leaves those tiles to the settle pass, which
+    walks the candidate grid for them (and renders rays with more intervals than the lists hold in windows only where a
+    bin exists -- here they are handed over).  Exact either way."""
+    uc = {"objects": {"objects": [{"type": "sphere", "center": [0.06, 0.06, 0.06], "radius": 0.035, "rho": 0.9},
+                                  {"type": "cylinder", "p0": [0.0, 0.06, 0.06], "p1": [0.12, 0.06, 0.06], "radius": 0.015, "rho": 0.5},
+                                  {"type": "cylinder", "p0": [0.06, 0.0, 0.03], "p1": [0.06, 0.12, 0.03], "radius": 0.012, "rho": 0.4}]},
+          "xmin": 0.0, "xmax": 0.12, "ymin": 0.0, "ymax": 0.12, "zmin": 0.0, "zmax": 0.12}
+    obj = {"type": "tessellated_obj_coll", "uc": uc, "xmin": -0.72, "xmax": 0.72, "ymin": -0.6, "ymax": 0.6, "zmin": -0.48, "zmax": 0.6}
+    views = ((17.0, 80.0), (90.0, 90.0), (45.0, 60.0))
+    for integ in ("hierarchical", "simple"):
+        out, nref, _ = gpu_vs_oracle(X, O, obj, views=views, res=32, ds=0.004, integ=integ)
+        assert_parity(out, nref)
+        st = out["fp32"][1]
+        assert st["span_renderer"] and st["launches"] >= 4
+        assert st["marched_tiles"] < 0.5 * len(views) * 4 * 4 * 2, st  # most warp tiles are rendered by the settle pass, not marched
+
+
 def test_span_matches_marching_kernels_at_benchmark_resolution(X, scenes, monkeypatch):
     """Full 1024^2 lattice view and a 1024^2 crop-equivalent of the pillar array: interval renderer versus the marching
     kernels, which the 1e-4 gate of the rest of the suite already ties to the oracle; same reference-equivalent sample count."""
