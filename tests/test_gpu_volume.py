@@ -425,3 +425,38 @@ def test_sparse_voxel_grid_nested_in_a_collection(X, O):
     for integ in ("hierarchical", "simple"):
         out, nref, _ = gpu_vs_oracle(X, O, obj, views=((0.0, 90.0), (33.0, 70.0), (90.0, 90.0)), res=32, ds=0.013, integ=integ)
         assert_parity(out, nref)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fp64_volume_kernel_random(X, O, seed):
+    """fp64 mode (<= 1e-9) over a voxel grid, both integrators, fp32 and fp64 voxels: the dedicated double-precision kernel
+    (per-cell cubic along the ray, evaluated at each lattice sample's own parameter) against the oracle, with the
+    reference-equivalent sample count; random shapes incl. single layers, sparse and mixed-sign data."""
+    rng = np.random.default_rng(6600 + seed)
+    shape = tuple(int(v) for v in rng.choice([1, 2, 3, 7, 16, 24, 33], 3))
+    vol = rng.random(shape)
+    if seed % 2:
+        vol -= 0.5
+    vol[rng.random(shape) < rng.choice([0.0, 0.5, 0.9, 0.99])] = 0.0
+    if seed % 3 == 0:
+        vol = np.round(vol * 4)
+    if seed % 4 < 2:
+        vol = vol.astype(np.float32)
+    views = [(float(rng.choice([0.0, 90.0, 45.0, rng.uniform(0, 360)])), float(rng.choice([90.0, rng.uniform(30, 150)]))) for _ in range(2)]
+    ds = float(rng.choice([0.05, 0.02, 0.011]))
+    dm = float(rng.choice([1.0, 0.6, -0.7, 0.0]))
+    ff = float(rng.choice([0.0, 0.1]))
+    res = int(rng.choice([16, 21, 32]))
+    cams = X.cameras_from_angles(views, R, FOV)
+    osc = O.OracleScene({"type": "voxel_grid", "_array": vol.astype(np.float64)}, flat_field=ff, density_multiplier=dm)
+    for integ in ("simple", "hierarchical"):
+        ref, nref = [], 0
+        for az, pol in views:
+            im, k = osc.render_view(*O.camera_from_angles(az, pol, R), res, FOV, R, ds, integ)
+            ref.append(im)
+            nref += k
+        ref = np.stack(ref)
+        img, st = X.render_volume(vol, cams, res, integration=integ, precision="fp64", ds=ds, flat_field=ff, density_multiplier=dm,
+                                  return_stats=True)
+        assert (np.abs(img.astype(np.float64) - ref) <= TOL_FP64 * np.maximum(1.0, ref)).all(), (integ, float(np.abs(img - ref).max()))
+        assert st["ref_samples"] == nref

@@ -17,6 +17,8 @@ bad = 0
 for seed in range(first, last):
     try:
         T.test_hierarchical_volume_kernel_random(X, O, seed)
+        if os.environ.get("SOAK_FP64"):
+            T.test_fp64_volume_kernel_random(X, O, seed)
         if os.environ.get("SOAK_SIMPLE"):
             rng = np.random.default_rng(880000 + seed)
             shape = tuple(int(v) for v in rng.choice([1, 2, 3, 5, 9, 20, 31], 3))

@@ -43,6 +43,8 @@ size_t span_kernel_smem_bytes(unsigned int section_bytes);
 cudaError_t launch_render_volume_tex(unsigned long long tex, const float* d_vol, int nx, int ny, int nz, const RenderParams& P,
                                      int warp_shape, const unsigned char* occ, int integrator, const unsigned char* d_nfine,
                                      cudaStream_t stream);
+cudaError_t launch_render_volume_f64(const void* d_vol, int dtype, int nx, int ny, int nz, const RenderParams& P, int integrator,
+                                     const unsigned char* d_nfine, cudaStream_t stream);
 size_t volume_brick_count(int nx, int ny, int nz);
 cudaError_t build_volume_occupancy(const float* d_vol, int nx, int ny, int nz, unsigned char* occ_a, unsigned char* occ_b,
                                    const unsigned char** result, unsigned long long surf, cudaStream_t stream);
@@ -654,7 +656,7 @@ static int run_job(Job& J) {
     // __ldg kernel when the array cannot be had (dimension limits: 2048 layers, 32768 x 32768 texels).
     bool use_tex = false;
     const unsigned char* vol_occ = nullptr;
-    if (J.fast_volume && !getenv("XRAY_VOLUME_LDG")) {
+    if (J.fast_volume && J.opts.precision == XRAY_PRECISION_FP32 && !getenv("XRAY_VOLUME_LDG")) {
         const int vx = h->voxel_dims[0][0], vy = h->voxel_dims[0][1], vz = h->voxel_dims[0][2];
         if (vz <= 2048 && vx <= 32768 && vy <= 32768) {
             if (C->vol_dims[0] != vx || C->vol_dims[1] != vy || C->vol_dims[2] != vz) {
@@ -825,11 +827,14 @@ static int run_job(Job& J) {
         }
     }
     auto launch_march = [&](cudaStream_t stream) -> cudaError_t {  // (shadows the job's stream on purpose)
+        if (J.fast_volume && J.opts.precision == XRAY_PRECISION_FP64)
+            return launch_render_volume_f64(ds->d_vox[0], J.scene->vox[0].dtype == XRAY_VOXEL_F64 ? 1 : 0, h->voxel_dims[0][0], h->voxel_dims[0][1],
+                                            h->voxel_dims[0][2], P, J.opts.integration == XRAY_INTEGRATE_HIERARCHICAL ? 1 : 0, C->d_nfine, stream);
         if (J.fast_volume && use_tex)
             return launch_render_volume_tex((unsigned long long)C->vol_tex, (const float*)ds->d_vox[0], h->voxel_dims[0][0],
                                             h->voxel_dims[0][1], h->voxel_dims[0][2], P, volume_warp_shape(J, (int)(P.cams - C->d_cams), P.n_views), vol_occ,
                                             J.opts.integration == XRAY_INTEGRATE_HIERARCHICAL ? 1 : 0, C->d_nfine, stream);
-        if (J.fast_volume && J.opts.integration == XRAY_INTEGRATE_SIMPLE)
+        if (J.fast_volume && J.opts.integration == XRAY_INTEGRATE_SIMPLE && J.scene->vox[0].dtype == XRAY_VOXEL_F32)
             return launch_render_volume_fast((const float*)ds->d_vox[0], h->voxel_dims[0][0], h->voxel_dims[0][1],
                                              h->voxel_dims[0][2], P, stream);
         if (J.opts.precision == XRAY_PRECISION_FP32 && shape != 0 && single_async && P.prog_in_smem && fast_kernel_smem_bytes(P) <= 200 * 1024)
@@ -1082,12 +1087,10 @@ static int render_common(XRayScene* scene, const XRayCameraParams64* cams, int n
     // misclassified sample.
     // A scene that is nothing but one fp32 voxel grid (a voxel_grid object file, no deformation) is what the volume entry
     // points build for themselves: it takes the dedicated voxel kernel from the scene entry points as well.
-    if (!fast_volume && scene->root.type == N_VOXEL && scene->deforms.empty() && h->n_voxel_slots == 1 && !borrowed_vox &&
-        scene->vox[0].data && scene->vox[0].dtype == XRAY_VOXEL_F32)
-        fast_volume = volume_fast_path_ok(opts, XRAY_VOXEL_F32);
+    if (!fast_volume && scene->root.type == N_VOXEL && scene->deforms.empty() && h->n_voxel_slots == 1 && !borrowed_vox && scene->vox[0].data)
+        fast_volume = volume_fast_path_ok(opts, scene->vox[0].dtype);
     if (opts.precision == XRAY_PRECISION_FP32 && !fp32_position_bound_ok(h, cams, n, res)) {
-        opts.precision = XRAY_PRECISION_FP64;
-        fast_volume = false;
+        opts.precision = XRAY_PRECISION_FP64;  // (a voxel scene keeps its dedicated kernel: the fp64 one)
     }
 
     std::vector<int> devs;
@@ -1354,7 +1357,8 @@ static int make_volume_scene(int nx, int ny, int nz, XRayScene** out) {
 
 static bool volume_fast_path_ok(const XRayRenderOpts& o, int dtype) {
     if (getenv("XRAY_VOLUME_GENERIC")) return false;
-    return dtype == XRAY_VOXEL_F32 && o.precision == XRAY_PRECISION_FP32;  // both integrators (hierarchical: the texture kernel only)
+    // fp32 mode: fp32 voxels, both integrators (hierarchical: the texture kernel only); fp64 mode: either voxel type
+    return o.precision == XRAY_PRECISION_FP64 || dtype == XRAY_VOXEL_F32;
 }
 
 extern "C" {

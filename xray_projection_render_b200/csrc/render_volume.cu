@@ -541,6 +541,197 @@ __global__ void __launch_bounds__(kBlockThreads, INTEG == 1 ? 6 : 8) render_volu
     add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, n_eval, valid ? 1ull : 0ull);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// fp64 mode (the <= 1e-9 verification mode) for a scene that is one voxel grid: the same cell-synchronous walk in double.
+// Within one cell the interpolant along the ray is a cubic in the ray parameter; its coefficients come from the eight
+// corners once per cell and every lattice sample of the cell costs a Horner step at its own parameter s_tab[k] - s_tab[k0]
+// (the lattice is NOT assumed uniform here: its repeated-addition drift of ~1e-12 would show at 1e-9).  Against the
+// reference's staged lerp the cubic differs by rounding only (~1e-15 relative), far inside the gate.  A sample the fp64
+// position puts within 1e-9 voxel of a cell face may be charged to the neighbouring cell: same value, the interpolant is
+// continuous.  Guard band at the cube's faces, the hierarchical integrator's zero tests and refinements: as in
+// render_volume_tex_kernel, with the reference's own expression (voxel_exact) wherever a decision is taken.
+// DT: 0 = fp32 voxels, 1 = fp64 voxels (objects.go:789-855 holds float64; the extended entry points accept either).
+// ---------------------------------------------------------------------------------------------------------
+template <int INTEG, int DT>
+__global__ void __launch_bounds__(kBlockThreads, 3) render_volume_f64_kernel(const RenderParams P, const void* __restrict__ vol, int nx, int ny,
+                                                                            int nz, const unsigned char* __restrict__ nfine) {
+    int view, i, j;
+    pixel_of_thread(P, blockIdx.x, threadIdx.x >> 5, view, i, j);
+    const bool valid = i < P.res && j < P.res;
+    if (!valid) { i = 0; j = 0; }
+    const Ray64 ray = make_ray(P.cams[view], i, j, P.res);
+    constexpr int OFF = INTEG == 1 ? 1 : 0;  // sample k sits at s_tab[k + OFF]
+    const double g = 1.0e-9;                 // guard band at the cube's faces (fp64 positions are good to ~1e-15)
+    const double lo_o[3] = {-1.0 - g, -1.0 - g, -1.0 - g}, hi_o[3] = {1.0 + g, 1.0 + g, 1.0 + g};
+    const double lo_i[3] = {-1.0 + g, -1.0 + g, -1.0 + g}, hi_i[3] = {1.0 - g, 1.0 - g, 1.0 - g};
+    double s_in, s_out, q_in, q_out;
+    const bool hit = valid && clip_ray(ray, lo_o, hi_o, s_in, s_out);
+    const bool hit_inner = hit && clip_ray(ray, lo_i, hi_i, q_in, q_out);
+    int k0, k1, m0 = 0, m1 = 0;
+    step_range(P, hit, s_in, s_out, OFF, k0, k1);
+    if (hit_inner) {
+        double a = ceil((q_in - P.smin) / P.ds) + 1.0 - (double)OFF, b = floor((q_out - P.smin) / P.ds) - 1.0 - (double)OFF;
+        a = fmin(fmax(a, (double)k0), (double)k1);
+        b = fmin(fmax(b + 1.0, a), (double)k1);
+        m0 = (int)a;
+        m1 = (int)b;
+    } else {
+        m0 = m1 = k0;
+    }
+    VoxelDev vd;
+    vd.data = vol;
+    vd.nx = nx;
+    vd.ny = ny;
+    vd.nz = nz;
+    vd.dtype = DT;
+    auto exact_at = [&](double s) -> double {
+        const double x = dadd(ray.o[0], dmul(ray.d[0], s));
+        const double y = dadd(ray.o[1], dmul(ray.d[1], s));
+        const double z = dadd(ray.o[2], dmul(ray.d[2], s));
+        return voxel_exact(vd, x, y, z);
+    };
+    unsigned int n_eval = 0, n_fallback = 0, n_fine = 0;
+    double tot = 0.0, corr = 0.0;
+    bool prev_z = true;  // prev_rho := 0.0 (main.go:179)
+    const bool dm_zero = P.dm == 0.0;
+    auto see = [&](int k, bool z) {  // coarse sample k of the hierarchical integrator is zero / is not: refine the interval on a flip
+        if (z != prev_z) {
+            const int nf = (int)__ldg(nfine + k);
+            double s = P.s_tab[k], fsum = 0.0;
+            for (int q = 0; q < nf; ++q) {
+                s = dadd(s, P.ds_fine);  // main.go:183,189
+                fsum += exact_at(s);
+            }
+            const double rk = z ? 0.0 : exact_at(P.s_tab[k + 1]);
+            corr += P.ds_fine * (fsum + rk) - P.ds * rk;
+            n_fine += (unsigned int)nf;
+            n_fallback += (unsigned int)nf + 1u;
+        }
+        prev_z = z;
+    };
+    if (hit) {
+        for (int k = k0; k < m0; ++k) {  // the entry face
+            const double r = exact_at(P.s_tab[k + OFF]);
+            tot += r;
+            if (INTEG == 1) see(k, dm_zero || dmul(r, P.dm) == 0.0);
+            ++n_eval;
+            ++n_fallback;
+        }
+    }
+    // the ray in index space, u(s) = ub + du * s (objects.go:796-801: (x + 1) / 2 * (N - 1))
+    const double hx = 0.5 * (double)(nx - 1), hy = 0.5 * (double)(ny - 1), hz = 0.5 * (double)(nz - 1);
+    const double ubx = (ray.o[0] + 1.0) * hx, uby = (ray.o[1] + 1.0) * hy, ubz = (ray.o[2] + 1.0) * hz;
+    const double dux = ray.d[0] * hx, duy = ray.d[1] * hy, duz = ray.d[2] * hz;
+    const double tolw = 1.0e-9;  // index-space distance to a cell face below which a sample's cell (hence its zero-ness) is in doubt
+    const size_t NY = (size_t)ny, NXY = (size_t)nx * ny;
+    const int kend = hit ? m1 : m0;
+    int k = m0;
+    while (k < kend) {
+        const double s0 = P.s_tab[k + OFF];
+        const double ux = fma(dux, s0, ubx), uy = fma(duy, s0, uby), uz = fma(duz, s0, ubz);
+        int x0 = max(0, min(nx - 1, (int)floor(ux))), y0 = max(0, min(ny - 1, (int)floor(uy))), z0 = max(0, min(nz - 1, (int)floor(uz)));
+        const double wx = ux - (double)x0, wy = uy - (double)y0, wz = uz - (double)z0;
+        // parameter length until the ray leaves the cell [x0, x0 + 1] x ... (an axis it does not move along never ends it)
+        double len = 1.0e300;
+        if (dux > 0.0) len = fmin(len, (1.0 - wx) / dux); else if (dux < 0.0) len = fmin(len, -wx / dux);
+        if (duy > 0.0) len = fmin(len, (1.0 - wy) / duy); else if (duy < 0.0) len = fmin(len, -wy / duy);
+        if (duz > 0.0) len = fmin(len, (1.0 - wz) / duz); else if (duz < 0.0) len = fmin(len, -wz / duz);
+        // samples k .. k + n - 1 lie before that point (at least this one; the count is settled on the lattice table itself)
+        int n = (int)fmin(fmax(len / P.ds, 0.0), 1.0e6) + 1;
+        n = max(1, min(n, kend - k));
+        while (n < kend - k && P.s_tab[k + n + OFF] - s0 < len) ++n;
+        while (n > 1 && P.s_tab[k + n - 1 + OFF] - s0 >= len) --n;
+        const int x1 = min(x0 + 1, nx - 1), y1 = min(y0 + 1, ny - 1), z1 = min(z0 + 1, nz - 1);
+#define XR_V(zz, xx, yy) (DT == 0 ? (double)__ldg((const float*)vol + ((size_t)(zz) * NXY + (size_t)(xx) * NY + (yy))) \
+                                  : __ldg((const double*)vol + ((size_t)(zz) * NXY + (size_t)(xx) * NY + (yy))))
+        const double v000 = XR_V(z0, x0, y0), v001 = XR_V(z1, x0, y0), v010 = XR_V(z0, x0, y1), v011 = XR_V(z1, x0, y1);
+        const double v100 = XR_V(z0, x1, y0), v101 = XR_V(z1, x1, y0), v110 = XR_V(z0, x1, y1), v111 = XR_V(z1, x1, y1);
+#undef XR_V
+        const bool zcell = v000 == 0.0 && v001 == 0.0 && v010 == 0.0 && v011 == 0.0 && v100 == 0.0 && v101 == 0.0 && v110 == 0.0 && v111 == 0.0;
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        if (!zcell) {
+            // f = v000 + ax X + ay Y + az Z + axy XY + axz XZ + ayz YZ + axyz XYZ; along the ray X = wx + dux tau, ...
+            const double ax = v100 - v000, ay = v010 - v000, az = v001 - v000;
+            const double bx = v101 - v001;
+            const double axy = (v110 - v010) - ax, axz = bx - ax, ayz = (v011 - v001) - ay;
+            const double axyz = ((v111 - v011) - bx) - axy;
+            const double tx = fma(wy, axyz, axz), ty = fma(wx, axyz, ayz), tz = fma(wz, axyz, axy);
+            const double gx = fma(wz, tx, fma(wy, axy, ax)), gy = fma(wz, ty, fma(wx, axy, ay)), gz = fma(wy, ty, fma(wx, axz, az));
+            c0 = fma(wx, gx, fma(wy, fma(wz, ayz, ay), fma(wz, az, v000)));
+            c1 = fma(dux, gx, fma(duy, gy, duz * gz));
+            c2 = fma(dux * duy, tz, fma(dux * duz, tx, duy * duz * ty));
+            c3 = axyz * dux * duy * duz;
+            double part = c0;  // sample 0 sits at tau = 0
+            for (int q = 1; q < n; ++q) {
+                const double tau = P.s_tab[k + q + OFF] - s0;
+                part += fma(tau, fma(tau, fma(tau, c3, c2), c1), c0);
+            }
+            tot += part;
+        }
+        if (INTEG == 1 && !dm_zero) {
+            // zero-ness of the n samples, in lattice order: sure inside a cell of zeros / of same-sign corners, away from the faces
+            const double vmin = fmin(fmin(fmin(v000, v001), fmin(v010, v011)), fmin(fmin(v100, v101), fmin(v110, v111)));
+            const double vmax = fmax(fmax(fmax(v000, v001), fmax(v010, v011)), fmax(fmax(v100, v101), fmax(v110, v111)));
+            const bool mixed = vmin < 0.0 && vmax > 0.0;
+            const double amax = fmax(-vmin, vmax);
+            for (int q = 0; q < n;) {
+                const double tau = P.s_tab[k + q + OFF] - s0;
+                const double px = fma(dux, tau, wx), py = fma(duy, tau, wy), pz = fma(duz, tau, wz);
+                const double dface = fmin(fmin(fmin(px, 1.0 - px), fmin(py, 1.0 - py)), fmin(pz, 1.0 - pz));
+                bool z, sure = dface > tolw;
+                if (sure && mixed) sure = fabs(fma(tau, fma(tau, fma(tau, c3, c2), c1), c0)) > 1.0e-9 * amax;
+                int adv = 1;
+                if (sure) {
+                    z = zcell;
+                    if (!mixed) {  // every later sample up to the last is as sure as this one and the last (w moves monotonically)
+                        const double tl = P.s_tab[k + n - 1 + OFF] - s0;
+                        const double lx = fma(dux, tl, wx), ly = fma(duy, tl, wy), lz = fma(duz, tl, wz);
+                        const double dl = fmin(fmin(fmin(lx, 1.0 - lx), fmin(ly, 1.0 - ly)), fmin(lz, 1.0 - lz));
+                        adv = dl > tolw ? n - q : 1;
+                    }
+                } else {
+                    ++n_fallback;
+                    z = dmul(exact_at(P.s_tab[k + q + OFF]), P.dm) == 0.0;
+                }
+                see(k + q, z);
+                q += adv;
+            }
+        }
+        k += n;
+    }
+    if (hit) n_eval += (unsigned int)(m1 - m0);
+    if (hit) {
+        for (int kk = m1; kk < k1; ++kk) {  // the exit face
+            const double r = exact_at(P.s_tab[kk + OFF]);
+            tot += r;
+            if (INTEG == 1) see(kk, dm_zero || dmul(r, P.dm) == 0.0);
+            ++n_eval;
+            ++n_fallback;
+        }
+        if (INTEG == 1 && k1 < P.n_steps) see(k1, true);  // the first sample beyond the cube is 0 (objects.go:795)
+    }
+    const double T = P.flat_field + (P.ds * tot + corr) * P.dm;
+    store_pixel(P, view, i, j, valid, exp(-T));
+    add_stats(P, valid ? (unsigned long long)P.n_steps + n_fine : 0ull, n_eval, n_fallback, n_eval, valid ? 1ull : 0ull);
+}
+
+cudaError_t launch_render_volume_f64(const void* d_vol, int dtype, int nx, int ny, int nz, const RenderParams& P, int integrator,
+                                     const unsigned char* d_nfine, cudaStream_t stream) {
+    const size_t grid = (size_t)P.n_views * P.tiles_i * P.tiles_j;
+    if (grid == 0) return cudaSuccess;
+    if (grid > 0x7fffffffull) return cudaErrorInvalidValue;
+    const unsigned int gsz = P.tile_list ? 0u : (unsigned int)grid;
+    if (gsz == 0u) return cudaErrorInvalidValue;  // (never used for the interval renderer's hand-over lists)
+    if (integrator == 0) {
+        if (dtype == 0) render_volume_f64_kernel<0, 0><<<gsz, kBlockThreads, 0, stream>>>(P, d_vol, nx, ny, nz, d_nfine);
+        else render_volume_f64_kernel<0, 1><<<gsz, kBlockThreads, 0, stream>>>(P, d_vol, nx, ny, nz, d_nfine);
+    } else {
+        if (dtype == 0) render_volume_f64_kernel<1, 0><<<gsz, kBlockThreads, 0, stream>>>(P, d_vol, nx, ny, nz, d_nfine);
+        else render_volume_f64_kernel<1, 1><<<gsz, kBlockThreads, 0, stream>>>(P, d_vol, nx, ny, nz, d_nfine);
+    }
+    return cudaGetLastError();
+}
+
 static const float kVolumeGuardTol = 4.0e-6f;  // fp32 position error (1e-6, scene_compile.cpp) with margin
 
 cudaError_t launch_render_volume_fast(const float* d_vol, int nx, int ny, int nz, const RenderParams& P, cudaStream_t stream) {
