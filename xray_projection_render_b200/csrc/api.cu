@@ -782,7 +782,8 @@ static int run_job(Job& J) {
     unsigned int bin_cap = 0, n_instances = 0;
     if (use_span && !getenv("XRAY_SPAN_NO_BINS")) {
         const SpanHeader* sh = (const SpanHeader*)(J.scene->blob.data() + h->span_off);
-        bool ok = !(sh->flags & SPAN_HAS_WARP);
+        const bool warped = (sh->flags & SPAN_HAS_WARP) != 0;
+        bool ok = !warped || sh->f_wscale > 0.0f;  // (an affine warp keeps the rays straight and through one point: bins in world space)
         for (int v = 0; v < nv && ok; ++v) {
             const XRayCameraParams64& c = J.cams[J.views[v]];
             const double* m = c.view;
@@ -797,8 +798,14 @@ static int run_job(Job& J) {
             // depth of the nearest corner of the scene's box along the optical axis (camera looks down -z)
             double dmin = 1e300;
             for (int q = 0; q < 8 && ok; ++q) {
+                double X[3];
+                for (int a = 0; a < 3; ++a) X[a] = sh->outer[(q >> a & 1) ? 3 + a : a];
+                if (warped) {  // the box is in warped space: its corner in the world
+                    const double u[3] = {X[0] - sh->warp_b[0], X[1] - sh->warp_b[1], X[2] - sh->warp_b[2]};
+                    for (int a = 0; a < 3; ++a) X[a] = sh->f_winv[a * 3 + 0] * u[0] + sh->f_winv[a * 3 + 1] * u[1] + sh->f_winv[a * 3 + 2] * u[2];
+                }
                 double d = 0.0;
-                for (int a = 0; a < 3; ++a) d -= m[a * 4 + 2] * (sh->outer[(q >> a & 1) ? 3 + a : a] - m[a * 4 + 3]);
+                for (int a = 0; a < 3; ++a) d -= m[a * 4 + 2] * (X[a] - m[a * 4 + 3]);
                 dmin = std::fmin(dmin, d);
             }
             ok = ok && dmin > 0.25;

@@ -12,7 +12,7 @@
 namespace xr {
 
 constexpr uint32_t kMagic = 0x58524159u;  // "XRAY"
-constexpr uint32_t kVersion = 7;
+constexpr uint32_t kVersion = 8;
 constexpr int kMaxVoxelSlots = 4;
 constexpr int kMaxSaveDepth = 6;  // nested save frames (collections/tessellations inside collections)
 constexpr int kFrameWords = 8;    // real-typed words per save frame
@@ -122,6 +122,9 @@ struct SpanHeader {
     double uc_hi[3];               // the unit cell's upper bounds as given (UnitCell.Density's inclusive test, objects.go:459)
     double warp_m[9], warp_b[3];   // object-space point = warp_m * world + warp_b (row-major), the composed affine warp
     float f_uc_lo[3], f_inv_cell[3], f_cell[3], f_pad[3];
+    // for the screen-space bins of a warped scene: world = f_winv * (object - warp_b) (row-major), and an upper bound of how
+    // much the inverse warp stretches lengths (Frobenius norm); f_wscale = 0: not invertible, no bins
+    float f_winv[9], f_wscale, f_pad2[2];
 };
 
 // 184 bytes per child.  p[]: sphere c(3) r2 | box c(3) h(3) | cylinder p0(3) v(3) 1/(v.v) r2 v.v |

@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) render_span_kernel(const 
         if (SETTLE) {
             unsigned int cb = 0u;  // this candidate's doubts
             const bool some = span_candidate_range<true>(H, K, ray, R0, px, py, pz, skip_axes, r, cb);
-            if (some && (cb & 0xffu) == 1u && nfz < kSpanFuzzCap) {  // the ray runs inside a plane of this child: settled below
+            if (some && (cb & 0xffu) == 1u && nfz < kSpanFuzzCap && !(flags & SPAN_HAS_WARP)) {  // the ray runs inside a plane of this child: settled below
                 fuzz[(nfz++) * kBlockThreads + tid] = code | 0x80000000u;
                 continue;
             }
@@ -1122,8 +1122,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) render_span_kernel(const 
     const bool tile_bad = __any_sync(FULL_MASK, bad);
     // fast pass: a warp tile whose only trouble is samples inside doubt zones goes to the settle pass, not to the marching kernels
     // (samples inside doubt zones; more intervals than the list holds, when the tile has a bin to take the candidates from)
-    const bool settleable = (doubt & ~(1u | 4u | 8u | 32u | 64u)) == 0u && (!(doubt & (8u | 32u)) || bl != nullptr);
-    const bool to_settle = !SETTLE && !(flags & SPAN_HAS_WARP) && tile_bad && !__any_sync(FULL_MASK, bad && !settleable);
+    // (under a warp nothing is settled exactly, but a tile whose bin overflowed still gets its grid walk there)
+    const bool settleable = (flags & SPAN_HAS_WARP) ? (doubt & ~64u) == 0u
+                                                    : ((doubt & ~(1u | 4u | 8u | 32u | 64u)) == 0u && (!(doubt & (8u | 32u)) || bl != nullptr));
+    const bool to_settle = !SETTLE && tile_bad && !__any_sync(FULL_MASK, bad && !settleable);
     if ((tid & 31) == 0 && tile_bad) {
         if (to_settle) {
             SA.settle_list[atomicAdd(SA.tile_count + 1, 1u)] = item;
@@ -1178,7 +1180,15 @@ __global__ void __launch_bounds__(kBlockThreads) span_bin_kernel(const RenderPar
     } else {
         ax = bx = K.bs[0] + sx; ay = by = K.bs[1] + sy; az = bz = K.bs[2] + sz;
     }
-    const float R = K.bs[3];
+    float R = K.bs[3];
+    if (H.flags & SPAN_HAS_WARP) {  // the children live in warped space: back to the world the camera sees (conservative radius)
+        const float* w = H.f_winv;
+        const float b0 = (float)H.warp_b[0], b1 = (float)H.warp_b[1], b2 = (float)H.warp_b[2];
+        const float ux = ax - b0, uy = ay - b1, uz = az - b2, vx = bx - b0, vy = by - b1, vz = bz - b2;
+        ax = w[0] * ux + w[1] * uy + w[2] * uz; ay = w[3] * ux + w[4] * uy + w[5] * uz; az = w[6] * ux + w[7] * uy + w[8] * uz;
+        bx = w[0] * vx + w[1] * vy + w[2] * vz; by = w[3] * vx + w[4] * vy + w[5] * vz; bz = w[6] * vx + w[7] * vy + w[8] * vz;
+        R = R * H.f_wscale + 1.0e-5f;
+    }
     // camera coordinates: X = V3 * cam + t  =>  cam = V3^T (X - t), V3 orthonormal (checked by the caller)
     const float tx = (float)cam.view[3], ty = (float)cam.view[7], tz = (float)cam.view[11];
     float ca[3], cb[3];

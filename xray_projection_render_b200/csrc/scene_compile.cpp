@@ -1467,6 +1467,22 @@ static bool build_span(const XRayScene& sc, std::vector<uint8_t>& out) {
         if (!std::isfinite(b[i])) return false;
         H.warp_b[i] = b[i];
     }
+    {  // inverse of the warp, for projecting the children onto the detector (span_bin_kernel)
+        const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+        H.f_wscale = 0.0f;
+        if (std::fabs(det) > 1e-6) {
+            const double inv[9] = {(M[4] * M[8] - M[5] * M[7]) / det, (M[2] * M[7] - M[1] * M[8]) / det, (M[1] * M[5] - M[2] * M[4]) / det,
+                                   (M[5] * M[6] - M[3] * M[8]) / det, (M[0] * M[8] - M[2] * M[6]) / det, (M[2] * M[3] - M[0] * M[5]) / det,
+                                   (M[3] * M[7] - M[4] * M[6]) / det, (M[1] * M[6] - M[0] * M[7]) / det, (M[0] * M[4] - M[1] * M[3]) / det};
+            double fro = 0.0;
+            for (int i = 0; i < 9; ++i) {
+                H.f_winv[i] = (float)inv[i];
+                fro += inv[i] * inv[i];
+            }
+            fro = std::sqrt(fro);
+            if (std::isfinite(fro) && fro < 1e3) H.f_wscale = (float)(fro * 1.0001);
+        }
+    }
 
     // region the candidate grid spans
     double lo[3], hi[3];
