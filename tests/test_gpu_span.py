@@ -66,8 +66,8 @@ def test_tangent_and_axis_parallel_rays(X, O):
 
 def test_more_intervals_than_the_lists_hold(X, O):
     """60 thin plates in a row: rays along the row cross more intervals than the per-ray lists of the interval renderer hold.
-    With screen-space bins the settle pass renders such rays in windows of the lattice (sweep state carried across windows);
-    under a warp (no bins: each ray walks the candidate grid) those tiles go to the marching kernels.  Exact either way."""
+    The settle pass renders such rays in windows of the lattice (sweep state carried across windows); under a warp nothing
+    is settled there, so those tiles go to the marching kernels.  Exact either way."""
     plates = [{"type": "box", "center": [-0.885 + 0.03 * k, 0.0, 0.0], "sides": [0.012, 0.8, 0.8], "rho": 0.05 + 0.01 * (k % 7)}
               for k in range(60)]
     obj = {"type": "object_collection", "objects": plates}
