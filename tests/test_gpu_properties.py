@@ -138,6 +138,34 @@ def test_device_resident_equals_host_path(X, scenes):
     assert np.array_equal(out64.cpu().numpy(), X.render_scene(sc, cams, 80, precision="fp64"))
 
 
+def test_pageable_output_at_any_alignment(X, scenes):
+    """The drain into the caller's pageable buffer (multi-threaded, streaming stores with a memcpy head and tail)
+    delivers the same bytes whatever the buffer's alignment, and writes nothing outside it (cuda_backend.go:294-337
+    hands over Go-heap slices)."""
+    sc = X.Scene(str(scenes / "balls.json"))
+    nv, res = 3, 1024  # 12.6 MB: three copy threads, every piece above the streaming threshold
+    cams = X.cameras_from_angles(X.generate_camera_angles(nv), R, FOV)
+    dev_ref = X.render_scene(sc, cams, res)
+    n = nv * res * res
+    for off in (1, 2, 3, 5):  # float32 elements: 4, 8, 12, 20 bytes past a 64-byte boundary
+        raw = np.full(n + 64, -7.0, dtype=np.float32)
+        base = (-raw.ctypes.data // 4) % 16  # element index of a 64-byte boundary
+        out = raw[base + off:base + off + n].reshape(nv, res, res)
+        assert out.ctypes.data % 64 == 4 * off
+        X.render_scene(sc, cams, res, out=out)
+        assert np.array_equal(out, dev_ref)
+        assert np.all(raw[:base + off] == -7.0) and np.all(raw[base + off + n:] == -7.0)
+    old = os.environ.get("XRAY_NO_STREAM_COPY")
+    os.environ["XRAY_NO_STREAM_COPY"] = "1"
+    try:
+        assert np.array_equal(X.render_scene(sc, cams, res), dev_ref)
+    finally:
+        if old is None:
+            del os.environ["XRAY_NO_STREAM_COPY"]
+        else:
+            os.environ["XRAY_NO_STREAM_COPY"] = old
+
+
 def test_multi_gpu_view_sharding_in_one_call(X, scenes):
     n = X._lib.load().XRayDeviceCount()
     if n < 2:

@@ -9,10 +9,15 @@
 // *Device* variant is used, 0 on success, small positive codes on failure, never exit/abort,
 // nothing printed to stdout, callable from any OS thread (device set explicitly per call).
 #include <cuda_runtime.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define XRAY_STREAM_COPY 1
+#endif
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,28 +134,74 @@ static void stage_release_locked() {
     g_stage_dev = -1;
 }
 
-// Host-side copy out of pinned staging into the caller's pageable buffer, split over a few threads: one core moves
+// Large host-to-host copy with streaming (non-temporal) stores. The staging copies move tens of megabytes that nobody
+// reads back soon; a cached store first reads the destination line for ownership, so memcpy's per-thread pieces (below
+// glibc's own non-temporal threshold) cost 3 bytes of DRAM traffic per byte copied where this costs 2. SSE2 is part of
+// the x86-64 baseline, so there is no dispatch; other hosts take memcpy. Measured with 8 threads on 64 MiB blocks:
+// 21-29 GB/s (memcpy) -> 29-40 GB/s.
+static void stream_copy(void* dst, const void* src, size_t n) {
+#ifdef XRAY_STREAM_COPY
+    if (n < ((size_t)256 << 10) || getenv("XRAY_NO_STREAM_COPY")) {
+        memcpy(dst, src, n);
+        return;
+    }
+    unsigned char* d = (unsigned char*)dst;
+    const unsigned char* s = (const unsigned char*)src;
+    const size_t head = (size_t)((16 - ((uintptr_t)d & 15)) & 15);
+    memcpy(d, s, head);
+    d += head;
+    s += head;
+    n -= head;
+    const size_t blocks = n >> 7;
+    for (size_t i = 0; i < blocks; ++i, s += 128, d += 128) {
+        const __m128i v0 = _mm_loadu_si128((const __m128i*)(s)), v1 = _mm_loadu_si128((const __m128i*)(s + 16));
+        const __m128i v2 = _mm_loadu_si128((const __m128i*)(s + 32)), v3 = _mm_loadu_si128((const __m128i*)(s + 48));
+        const __m128i v4 = _mm_loadu_si128((const __m128i*)(s + 64)), v5 = _mm_loadu_si128((const __m128i*)(s + 80));
+        const __m128i v6 = _mm_loadu_si128((const __m128i*)(s + 96)), v7 = _mm_loadu_si128((const __m128i*)(s + 112));
+        _mm_stream_si128((__m128i*)(d), v0);
+        _mm_stream_si128((__m128i*)(d + 16), v1);
+        _mm_stream_si128((__m128i*)(d + 32), v2);
+        _mm_stream_si128((__m128i*)(d + 48), v3);
+        _mm_stream_si128((__m128i*)(d + 64), v4);
+        _mm_stream_si128((__m128i*)(d + 80), v5);
+        _mm_stream_si128((__m128i*)(d + 96), v6);
+        _mm_stream_si128((__m128i*)(d + 112), v7);
+    }
+    _mm_sfence();  // the streamed lines are globally visible before anyone (a DMA engine, the caller) is told so
+    memcpy(d, s, n & 127);
+#else
+    memcpy(dst, src, n);
+#endif
+}
+
+// Host-side copy out of pinned staging into the caller's pageable buffer, split over the host's cores: one core moves
 // ~8-10 GB/s, the PCIe link delivers ~55, and a cgo / ctypes caller always hands over pageable memory.
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    int T = (int)std::min<size_t>(8, std::max<size_t>(1, bytes / ((size_t)4 << 20)));
+    int T = (int)std::min<size_t>(16, std::max<size_t>(1, bytes / ((size_t)4 << 20)));
     unsigned hc = std::thread::hardware_concurrency();
+    bool shared_host = false;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU (torchrun): the ranks share the host's cores
         const int lw = atoi(e);
-        if (lw > 1) hc = std::max(1u, hc / (unsigned)lw);
+        if (lw > 1) {
+            hc = std::max(1u, hc / (unsigned)lw);
+            shared_host = true;
+        }
     }
-    if (hc > 0) T = std::min<int>(T, std::max(1u, hc / 2));
+    // A lone caller is blocked in this call, so every core may copy (16-core host, 64 MiB blocks: 8 threads 20.3 ms,
+    // 12 threads 18.8, 16 threads 17.6 per 512 MB of images); ranks sharing a host keep half their share.
+    if (hc > 0) T = std::min<int>(T, std::max(1u, shared_host ? hc / 2 : hc));
     if (const char* e = getenv("XRAY_DRAIN_THREADS")) T = std::max(1, std::min(32, atoi(e)));
     if (T <= 1) {
-        memcpy(dst, src, bytes);
+        stream_copy(dst, src, bytes);
         return;
     }
     std::vector<std::thread> th;
     const size_t per = ((bytes / T) + 4095) & ~(size_t)4095;
     for (int t = 1; t < T; ++t) {
         const size_t off = std::min(bytes, per * t), end = std::min(bytes, per * (t + 1));
-        if (end > off) th.emplace_back([=] { memcpy((unsigned char*)dst + off, (const unsigned char*)src + off, end - off); });
+        if (end > off) th.emplace_back([=] { stream_copy((unsigned char*)dst + off, (const unsigned char*)src + off, end - off); });
     }
-    memcpy(dst, src, std::min(bytes, per));
+    stream_copy(dst, src, std::min(bytes, per));
     for (auto& t : th) t.join();
 }
 
@@ -196,7 +247,7 @@ static cudaError_t upload_h2d(void* d_dst, const void* h_src, size_t bytes, int 
                 const size_t n = std::min(kStageChunk, hi - off);
                 e = cudaEventSynchronize(ev[b]);  // the previous copy out of this buffer is done (no-op the first time)
                 if (e != cudaSuccess) break;
-                memcpy(g_stage_buf[t][b], (const unsigned char*)h_src + off, n);
+                stream_copy(g_stage_buf[t][b], (const unsigned char*)h_src + off, n);
                 e = cudaMemcpyAsync((unsigned char*)d_dst + off, g_stage_buf[t][b], n, cudaMemcpyHostToDevice, st);
                 if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
             }
