@@ -8,17 +8,24 @@
 // Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off matters: Go/amd64 never fuses a*b+c, so neither may we.
 //
-// PARITY STATUS: the reference is Go and no Go toolchain exists in this image, so
-// this restatement cannot be diffed against the reference binary.  It is pinned
-// against every known-answer case of the reference's own unit tests
-// (main_test.go, objects/objects_test.go, deformations/deformations_test.go; see
-// tests/test_oracle_known_answers.py) and against an independent numpy
-// restatement (tests/test_oracle_vs_numpy.py).  The camera matrix
-// (mgl64.LookAtV(...).Inv()) and Parallelepiped (mgl64.Mat3.Inv) come from the
-// un-vendored dependency github.com/go-gl/mathgl v1.1.0 (go.mod:6); they are
-// restated from its published algorithm and are "parity unpinned" beyond the
-// invariants asserted in the tests (camera*(0,0,0,1)=eye, orthonormal columns,
-// M*Minv=I).
+// PARITY STATUS: PINNED AGAINST OUTPUT OF THE REFERENCE'S GO BINARY.  No Go toolchain
+// exists in this image, but the reference repository carries one rendered image: the
+// cell output stored in examples/demo.ipynb (three 300 x 300 projections of
+// cube_w_hole.yaml).  This restatement reproduces all 270 000 of its pixels (52 067
+// attenuated, 154 grey levels) exactly -- camera from angles, pixel -> ray, the
+// hierarchical integrator with its refinements, collection / cube / sphere / cylinder
+// densities with negative rho, exp(-T), 8-bit quantisation and y flip -- and no nearby
+// parameter or convention does (tests/test_reference_go_output.py; fixture and extraction
+// script under tests/golden/).  It is further pinned against every known-answer case of
+// the reference's own unit tests (main_test.go, objects/objects_test.go,
+// deformations/deformations_test.go; tests/test_oracle_known_answers.py), against an
+// independent pure-Python restatement (tests/test_oracle_vs_python.py), and -- camera use,
+// pixel mapping, layouts, voxeliser -- against the reference's own CUDA plugin built from
+// /root/reference (tests/test_gpu_reference_pin.py).
+// What the stored image does not exercise stays pinned only by the reference's unit-test
+// answers and invariants: polar angles other than 90 degrees, Parallelepiped
+// (mgl64.Mat3.Inv, from the un-vendored github.com/go-gl/mathgl v1.1.0, go.mod:6;
+// M*Minv=I asserted), gyroid, tessellation, voxel grids and the deformations.
 //
 // Every function cites the reference file:line it follows.
 
