@@ -521,6 +521,27 @@ def measure(X, torch, dist, name, rank, world, local_rank, steps, warmup, flush,
     return rec
 
 
+def go_output_pin(X):
+    """Not timed.  The one image the reference repository holds that its Go binary rendered (the cell output stored in
+    examples/demo.ipynb: three 300 x 300 views of cube_w_hole; fixture under tests/golden/, see
+    tests/test_reference_go_output.py) rendered again through the C ABI and compared as 8-bit grey levels."""
+    try:
+        stored = np.load(ROOT / "tests" / "golden" / "reference_go_cube_w_hole_3x300.npz")["image"]
+        sc = X.Scene(str(SCENES / "cube_w_hole.json"))
+        cams = X.cameras_from_angles(X.generate_camera_angles(3), 5.0, 45.0)
+        out = {}
+        for prec in ("fp64", "fp32"):
+            imgs = X.render_scene(sc, cams, 300, precision=prec, ds=0.1, integration="hierarchical")
+            grey = np.hstack([X.image_to_rgba8(np.asarray(v, dtype=np.float64))[..., 0] for v in imgs])
+            d = np.abs(grey.astype(int) - stored.astype(int))
+            out[prec] = {"pixels_differing": int((d != 0).sum()), "max_grey_level_difference": int(d.max())}
+        return {"against": "output of the reference's Go binary: image stored in examples/demo.ipynb (3 views of cube_w_hole at 300x300; R=5, fov=45, "
+                           "ds=0.1, hierarchical reproduce it exactly on the CPU oracle)",
+                "pixels": int(stored.size), "attenuated_pixels": int((stored < 255).sum()), **out}
+    except Exception as e:  # the pin is evidence beside the measurement, never a reason to lose the line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 SUB_CONFIGS = (  # (key, workload, views rendered on N = 1)
     ("cfg1", "cube_w_hole", 1), ("cfg3", "gyroid_sigmoid", 90), ("cfg4", "voxel1024", 16), ("cfg5", "pillar_array", 8))
 
@@ -586,6 +607,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for r in subs.values():
             r.pop("clocks", None)
         line["configs"] = subs
+    if world == 1:
+        line["reference_output_pin"] = go_output_pin(X)
     if world == 1 and not args.no_cpu:
         cb = cpu_baseline(args.workload, budget_s=args.cpu_budget, volume=volume if is_volume else None)
         line["cpu_baseline"] = {"value": cb["gsamples_per_s"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": cb["kind"],
