@@ -227,3 +227,46 @@ def test_voxeliser_overlapping_and_degenerate_cylinders_vs_reference(X, ref):
         assert ref.AssembleVoxelGridCUDA(arr, len(cyls), res, ctypes.c_float(dm), want.ctypes.data_as(fp)) == 0
         assert L.AssembleVoxelGridCUDA(arr, len(cyls), res, ctypes.c_float(dm), got.ctypes.data_as(fp)) == 0
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{(got != want).sum()} voxels differ"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_tile_culled_voxeliser_random_cylinders_vs_reference(X, ref, seed):
+    """The brute-force symbol culls the cylinder list per 4 x 8 x 8 voxel tile before the per-voxel test
+    (misc_kernels.cu); every voxel must still equal the reference's all-pairs kernel bit for bit: random segments of all
+    lengths and radii (incl. tiny, huge, reversed, negative radius and rho, far outside the volume), res not a multiple
+    of the tile, and enough cylinders through one place that the shared-memory list is flushed mid-way (> 1024)."""
+    L = X._lib.load()
+    rng = np.random.default_rng(100 + seed)
+    n = [300, 2500, 1500, 40][seed]
+    res = [77, 61, 40, 130][seed]
+    arr = (X._lib.CylinderParams * n)()
+    for k in range(n):
+        if seed == 1 and k % 2 == 0:   # a sheaf through the same point: > 1024 survivors in the tiles around it
+            c = np.array([0.13, -0.21, 0.34])
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            p0, p1 = c - d * rng.uniform(0.05, 1.5), c + d * rng.uniform(0.05, 1.5)
+            r = rng.uniform(0.01, 0.05)
+        else:
+            p0 = rng.uniform(-1.4, 1.4, 3)
+            p1 = p0 + rng.normal(size=3) * rng.choice([1e-6, 0.02, 0.3, 1.0, 3.0])
+            r = rng.choice([1e-4, 0.01, 0.05, 0.2, 0.7]) * rng.uniform(0.5, 1.5)
+        if k % 17 == 0:
+            r = -r          # the test compares with r*r
+        if k % 23 == 0:
+            p1 = p0.copy()  # zero length: skipped
+        if k % 29 == 0:
+            p0, p1 = p0 * 40.0, p1 * 40.0   # far away
+        arr[k].p0[:] = [float(v) for v in p0]
+        arr[k].p1[:] = [float(v) for v in p1]
+        arr[k].radius = float(r)
+        arr[k].rho = float(rng.choice([0.3, 0.05, -0.2, 1.0]) * rng.uniform(0.5, 1.0))
+    fp = ctypes.POINTER(ctypes.c_float)
+    dm = [1.0, 0.02, 0.7, -1.0][seed]
+    want = np.zeros((res, res, res), dtype=np.float32)
+    got = np.full_like(want, -1.0)
+    assert ref.AssembleVoxelGridCUDA(arr, n, res, ctypes.c_float(dm), want.ctypes.data_as(fp)) == 0
+    assert L.AssembleVoxelGridCUDA(arr, n, res, ctypes.c_float(dm), got.ctypes.data_as(fp)) == 0
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{(got != want).sum()} voxels differ"
+    if seed < 3:
+        assert 0.0 < (want > 0).mean() < 1.0

@@ -13,7 +13,7 @@ LIB = ROOT / "xray_projection_render_b200" / "lib" / "libcuda_render.so"
 HOT = [r"render_span_kernel<\(int\)1, \(bool\)0, \(bool\)0, \(bool\)0, \(int\)5>", r"render_span_kernel<\(int\)1, \(bool\)0, \(bool\)1, \(bool\)1, \(int\)4>",
        r"span_bin_kernel", r"render_async_kernel<\(int\)2, \(int\)1, \(bool\)0, \(int\)5>", r"render_fast_kernel<\(int\)2, \(int\)1, \(bool\)0, \(bool\)0, \(int\)3>",
        r"render_volume_tex_kernel<\(int\)32, \(int\)1, \(int\)0>", r"render_volume_tex_kernel<\(int\)32, \(int\)1, \(int\)1>",
-       r"render_volume_f64_kernel<\(int\)0, \(int\)0>", r"render_scene_exact_kernel", r"voxelize_cyl_kernel"]
+       r"render_volume_f64_kernel<\(int\)0, \(int\)0>", r"render_scene_exact_kernel", r"voxelize_tiles_kernel", r"voxelize_cells_kernel"]
 
 
 def demangle(names):
