@@ -187,9 +187,10 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
             shared_host = true;
         }
     }
-    // A lone caller is blocked in this call, so every core may copy (16-core host, 64 MiB blocks: 8 threads 20.3 ms,
-    // 12 threads 18.8, 16 threads 17.6 per 512 MB of images); ranks sharing a host keep half their share.
-    if (hc > 0) T = std::min<int>(T, std::max(1u, shared_host ? hc / 2 : hc));
+    // The caller is blocked in this call, so every core of its share may copy (16-core host, 64 MiB blocks: 8 threads
+    // 20.3 ms, 12 threads 18.8, 16 threads 17.6 per 512 MB of images; two ranks on that host: 4 / 8 / 16 threads per rank
+    // give 4895 / 5080 / 5140 Gsamples/s end to end on the lattice, 1649 / 1707 / 1804 on the pillar array).
+    if (hc > 0) T = std::min<int>(T, std::max(shared_host ? 2u : 1u, hc));
     if (const char* e = getenv("XRAY_DRAIN_THREADS")) T = std::max(1, std::min(32, atoi(e)));
     if (T <= 1) {
         stream_copy(dst, src, bytes);
