@@ -229,6 +229,9 @@ def test_generate_camera_angles_and_sharding(X):
     assert seen == sorted(x["azimuthal"] for x in X.generate_camera_angles(10))
     assert [len(s) for s in shards] == [3, 3, 2, 2]
     assert X.parse_float_list("1, 2.5 ,3") == [1.0, 2.5, 3.0] and X.parse_float_list("") == []
+    assert X.parse_float_list("90,,180, ") == [90.0, 180.0]  # main.go:268-270 skips empty fields
+    with pytest.raises(ValueError, match="invalid float value 'x'"):
+        X.parse_float_list("1,x")
 
 
 def test_legacy_camera_narrowing_roundtrip(X):

@@ -32,7 +32,16 @@ def parse_float_list(s: str) -> list[float]:
     """main.go:260-275 parseFloatList."""
     if s == "":
         return []
-    return [float(p.strip()) for p in s.split(",")]
+    out = []
+    for part in s.split(","):
+        part = part.strip()
+        if part == "":  # main.go:268-270: empty fields are skipped, not errors
+            continue
+        try:
+            out.append(float(part))
+        except ValueError:
+            raise ValueError(f"invalid float value '{part}'") from None
+    return out
 
 
 def camera_from_angles(azimuthal_deg: float, polar_deg: float, R: float, fov_deg: float = 40.0) -> _lib.XRayCameraParams64:
