@@ -111,3 +111,141 @@ def test_python_twin_reproduces_columns_without_the_oracle(stored):
                 wrong += int(grey != int(stored[RES_NB - 1 - j, view * RES_NB + i]))
     assert checked == 3 * 3 * 43
     assert wrong <= 2, wrong  # the twin's camera rounds differently from mgl64 in the last bit: a grey-level boundary may fall between
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Goldens from a Go toolchain, wherever one exists: tools/make_go_goldens.sh renders tests/golden/go/cases.json with the
+# reference CLI and drops the PNG frames beside it.  The build image has no Go, so none are committed; the hook below
+# compares whatever is present and the two tests after it keep the hook itself honest.
+# ---------------------------------------------------------------------------------------------------------------------
+def png_decode_grey(data: bytes) -> np.ndarray:
+    """8-bit PNG (colour type 0 grey, 2 RGB or 6 RGBA, any row filter -- Go's encoder picks filters adaptively) -> the
+    grey level [h, w]; colour images must have R = G = B (main.go:495-497 writes val three times)."""
+    import struct
+    import zlib
+
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, hdr = 8, [], None
+    while pos < len(data):
+        (n,), tag = struct.unpack(">I", data[pos:pos + 4]), data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        if tag == b"IHDR":
+            hdr = struct.unpack(">IIBBBBB", body)
+        elif tag == b"IDAT":
+            idat.append(body)
+        pos += 12 + n
+    w, h, depth, ctype, _, _, interlace = hdr
+    assert depth == 8 and interlace == 0 and ctype in (0, 2, 6), hdr
+    bpp = {0: 1, 2: 3, 6: 4}[ctype]
+    raw = zlib.decompress(b"".join(idat))
+    stride = w * bpp
+    out = np.zeros((h, stride), dtype=np.uint8)
+    prev = np.zeros(stride, dtype=np.int64)
+    for y in range(h):
+        f = raw[y * (stride + 1)]
+        line = np.frombuffer(raw, dtype=np.uint8, count=stride, offset=y * (stride + 1) + 1).astype(np.int64)
+        if f == 0:
+            cur = line
+        elif f == 2:
+            cur = (line + prev) & 255
+        else:
+            cur = np.zeros(stride, dtype=np.int64)
+            for x in range(stride):
+                a = int(cur[x - bpp]) if x >= bpp else 0
+                b = int(prev[x])
+                c = int(prev[x - bpp]) if x >= bpp else 0
+                if f == 1:
+                    p = a
+                elif f == 3:
+                    p = (a + b) >> 1
+                else:
+                    pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+                    p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                cur[x] = (int(line[x]) + p) & 255
+        out[y] = cur
+        prev = cur
+    px = out.reshape(h, w, bpp)
+    if bpp >= 3:
+        assert np.array_equal(px[..., 0], px[..., 1]) and np.array_equal(px[..., 0], px[..., 2])
+    return np.ascontiguousarray(px[..., 0])
+
+
+def go_case_differences(O, to_grey, case: dict, directory) -> tuple[int, int] | None:
+    """(pixels that differ, largest grey-level difference) of one case against the oracle; None when its frames are absent."""
+    from pathlib import Path
+
+    files = [Path(directory) / f"{case['name']}_{k:03d}.png" for k in range(len(case["azimuthal"]))]
+    if not all(f.exists() for f in files):
+        return None
+    stem = case["input"].rsplit(".", 1)[0]
+    deform = str(SCENES / (case["deformation"].rsplit(".", 1)[0] + ".json")) if case["deformation"] else None
+    osc = O.OracleScene(str(SCENES / f"{stem}.json"), deform, flat_field=case["flat_field"], density_multiplier=case["density_multiplier"])
+    ds = case["ds"] if case["ds"] > 0 else osc.auto_ds()  # main.go:350-353
+    ndiff = worst = 0
+    for f, az, polar in zip(files, case["azimuthal"], case["polar"]):
+        eye, cm = O.camera_from_angles(az, polar, case["R"])
+        img, _ = osc.render_view(eye, cm, case["resolution"], case["fov"], case["R"], ds, case["integration"])
+        d = np.abs(to_grey(img).astype(int) - png_decode_grey(f.read_bytes()).astype(int))
+        ndiff += int((d != 0).sum())
+        worst = max(worst, int(d.max()))
+    return ndiff, worst
+
+
+def _go_cases():
+    import json
+
+    return json.loads((GOLDEN / "go" / "cases.json").read_text())["cases"]
+
+
+def test_go_goldens_when_present(O, to_grey):
+    checked = []
+    for case in _go_cases():
+        r = go_case_differences(O, to_grey, case, GOLDEN / "go")
+        if r is None:
+            continue
+        ndiff, worst = r
+        allowed = max(2, case["resolution"] ** 2 * len(case["azimuthal"]) // 500) if case["libm"] else 0
+        assert ndiff <= allowed and worst <= 1, (case["name"], ndiff, worst)
+        checked.append(case["name"])
+    if not checked:
+        pytest.skip("no Go-made goldens under tests/golden/go/ (tools/make_go_goldens.sh needs a Go toolchain; the image has none)")
+
+
+def test_png_decoder_on_the_notebook_image(stored):
+    """The decoder the hook relies on, against PIL's reading of the stored notebook PNG (the .npz was written through PIL)."""
+    got = png_decode_grey((GOLDEN / "reference_go_cube_w_hole_3x300.png").read_bytes())
+    assert np.array_equal(got, stored)
+
+
+def test_go_golden_hook_accepts_and_rejects(O, to_grey, tmp_path):
+    """The hook itself: frames written in the Go layout from oracle renders of two cases pass with 0 differences, and a
+    frame of the wrong view, or one with a single changed pixel, is caught."""
+    from xray_projection_render_b200.renderer import image_to_rgba8, write_png
+
+    cases = {c["name"]: c for c in _go_cases()}
+    for name in ("cube_polar", "cube_simple_ff"):
+        c = cases[name]
+        stem = c["input"].rsplit(".", 1)[0]
+        osc = O.OracleScene(str(SCENES / f"{stem}.json"), None, flat_field=c["flat_field"], density_multiplier=c["density_multiplier"])
+        ds = c["ds"] if c["ds"] > 0 else osc.auto_ds()
+        for k, (az, polar) in enumerate(zip(c["azimuthal"], c["polar"])):
+            eye, cm = O.camera_from_angles(az, polar, c["R"])
+            img, _ = osc.render_view(eye, cm, c["resolution"], c["fov"], c["R"], ds, c["integration"])
+            write_png(str(tmp_path / f"{name}_{k:03d}.png"), image_to_rgba8(np.asarray(img)))
+        assert go_case_differences(O, to_grey, c, tmp_path) == (0, 0)
+    assert go_case_differences(O, to_grey, cases["balls"], tmp_path) is None  # frames absent
+    c = cases["cube_polar"]
+    a, b = tmp_path / "cube_polar_000.png", tmp_path / "cube_polar_001.png"
+    blob_a, blob_b = a.read_bytes(), b.read_bytes()
+    a.write_bytes(blob_b)
+    b.write_bytes(blob_a)
+    ndiff, _ = go_case_differences(O, to_grey, c, tmp_path)
+    assert ndiff > 1000  # views swapped
+    a.write_bytes(blob_a)
+    b.write_bytes(blob_b)
+    grey = png_decode_grey(blob_a).copy()
+    grey[40, 50] ^= 1
+    rgba = np.repeat(grey[..., None], 4, axis=2)
+    rgba[..., 3] = 255
+    write_png(str(a), rgba)
+    assert go_case_differences(O, to_grey, c, tmp_path) == (1, 1)
