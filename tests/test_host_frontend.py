@@ -328,3 +328,16 @@ def test_gyroid_second_order_bound_in_the_program(X):
               {"type": "composed", "deformations": [{"type": "rigid", "displacements": [0.1, 0.0, 0.0]},
                                                     {"type": "linear", "strains": [0.01, 0.02, 0.03, 0.0, 0.0, 0.05]}]}):
         assert _gyroid_records(X, cell, d)[1][0] == 0.0  # exactly: the kernel tests `> 0`
+
+
+def test_scene_compiler_survives_malformed_json():
+    """Contract of the plugin boundary (api.cu header; cuda_backend.cu never exits either): whatever bytes arrive, the
+    compiler returns a code.  2000 malformed variants of the bundled scenes, in a subprocess so that a crash is a failure."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    script = Path(__file__).resolve().parent / "dev" / "fuzz_compile.py"
+    r = subprocess.run([sys.executable, str(script), "11", "2000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    assert "2000 inputs" in r.stdout and " compiled, " in r.stdout
