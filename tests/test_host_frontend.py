@@ -341,3 +341,16 @@ def test_scene_compiler_survives_malformed_json():
     r = subprocess.run([sys.executable, str(script), "11", "2000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     assert "2000 inputs" in r.stdout and " compiled, " in r.stdout
+
+
+def test_scene_compiler_survives_edge_values():
+    """Well-formed scenes with degenerate numbers (zero-size unit cells, zero / negative radii, 1e308 extents, denormals): the
+    compiler answers promptly with 0 or an error code -- no crash, no runaway candidate-grid construction."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    script = Path(__file__).resolve().parent / "dev" / "fuzz_compile_values.py"
+    r = subprocess.run([sys.executable, str(script), "21", "1200"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    assert "1200 inputs" in r.stdout and ", 0 slow" in r.stdout, r.stdout[-500:]
