@@ -75,3 +75,32 @@ def test_device_resident_path_reproduces_the_go_binary(X, scenes, stored):
     torch.cuda.synchronize()
     d = np.abs(grey_strip(X, out.cpu().numpy()).astype(int) - stored.astype(int))
     assert d.max() <= 1 and int((d != 0).sum()) <= 2
+
+
+def test_go_goldens_when_present_through_the_cuda_path(X, scenes):
+    """Frames made by the reference CLI on a machine with Go (tools/make_go_goldens.sh -> tests/golden/go/), compared
+    directly with fp64-mode renders through the C ABI.  None can be made in the build image, so this skips there."""
+    import json
+
+    from test_reference_go_output import png_decode_grey
+
+    checked = 0
+    for c in json.loads((GOLDEN / "go" / "cases.json").read_text())["cases"]:
+        files = [GOLDEN / "go" / f"{c['name']}_{k:03d}.png" for k in range(len(c["azimuthal"]))]
+        if not all(f.exists() for f in files):
+            continue
+        deform = str(scenes / (c["deformation"].rsplit(".", 1)[0] + ".json")) if c["deformation"] else None
+        sc = X.Scene(str(scenes / (c["input"].rsplit(".", 1)[0] + ".json")), deform)
+        cams = X.cameras_from_angles(list(zip(c["azimuthal"], c["polar"])), c["R"], c["fov"])
+        imgs = X.render_scene(sc, cams, c["resolution"], precision="fp64", ds=c["ds"], integration=c["integration"],
+                              flat_field=c["flat_field"], density_multiplier=c["density_multiplier"])
+        ndiff = worst = 0
+        for f, im in zip(files, imgs):
+            d = np.abs(X.image_to_rgba8(im)[..., 0].astype(int) - png_decode_grey(f.read_bytes()).astype(int))
+            ndiff += int((d != 0).sum())
+            worst = max(worst, int(d.max()))
+        allowed = max(2, c["resolution"] ** 2 * len(c["azimuthal"]) // 500) if c["libm"] else 2
+        assert ndiff <= allowed and worst <= 1, (c["name"], ndiff, worst)
+        checked += 1
+    if not checked:
+        pytest.skip("no Go-made goldens under tests/golden/go/")
