@@ -3,6 +3,9 @@
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
 ``--impl reference`` legs may import this module.  The product package never does.
 
+Parity status: pinned against output of the reference's Go binary (the image stored in the reference's demo notebook,
+reproduced bit for bit -- tests/test_reference_go_output.py); details in the header of xray_oracle.cpp.
+
 The oracle receives scenes as a token stream (hex floats, bit exact) that this module
 derives from the same ``map[string]interface{}`` shaped dict the reference's ``FromMap``
 methods consume (objects/objects.go, deformations/deformations.go).
