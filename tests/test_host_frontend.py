@@ -354,3 +354,50 @@ def test_scene_compiler_survives_edge_values():
     r = subprocess.run([sys.executable, str(script), "21", "1200"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     assert "1200 inputs" in r.stdout and ", 0 slow" in r.stdout, r.stdout[-500:]
+
+
+def test_renderer_batches_views_and_threads_the_png_writes(X, scenes, tmp_path, monkeypatch):
+    """XRayRenderer.render pushes the views through the library in bounded batches and encodes frames on a thread pool;
+    file names, bytes, frame order and transforms.json must not depend on the batching.  The library call is replaced by
+    a stub here (no GPU in the CPU suite); tests/test_gpu_properties.py and test_gpu_reference_go_output.py run the real one."""
+    import hashlib
+    import json
+
+    import xray_projection_render_b200.renderer as RR
+
+    calls = []
+
+    def fake_render_scene(scene, cams, res, **kw):
+        calls.append(len(cams))
+        out = np.empty((len(cams), res, res), dtype=np.float32)
+        ii, jj = np.meshgrid(np.arange(res), np.arange(res), indexing="ij")
+        for k, c in enumerate(cams):
+            phase = float(c.view[3]) + 2.0 * float(c.view[7])  # the eye position: differs per view
+            out[k] = 0.5 + 0.5 * np.sin(0.37 * ii + 0.11 * jj + phase)
+        return out
+
+    monkeypatch.setattr(RR, "render_scene", fake_render_scene)
+    digests = {}
+    for label, batch_bytes in (("one_batch", 1 << 30), ("two_views_per_batch", 2 * 40 * 40 * 4), ("one_view_per_batch", 1)):
+        calls.clear()
+        out_dir = tmp_path / label / "images"
+        r = X.XRayRenderer()
+        monkeypatch.setattr(r, "RENDER_BATCH_BYTES", batch_bytes, raising=False)
+        res = r.render({"input": str(scenes / "cube_w_hole.json"), "output_dir": str(out_dir), "resolution": 40, "num_images": 7,
+                        "transforms_file": str(tmp_path / label / "transforms.json")})
+        assert res["success"] and res["rendered"] == 7
+        assert calls == {"one_batch": [7], "two_views_per_batch": [2, 2, 2, 1], "one_view_per_batch": [1] * 7}[label]
+        files = sorted(p.name for p in out_dir.iterdir())
+        assert files == [f"image_{k:03d}.png" for k in range(7)]
+        tf = json.loads((tmp_path / label / "transforms.json").read_text())
+        assert [f["file_path"] for f in tf["frames"]] == [f"images/image_{k:03d}.png" for k in range(7)]
+        digests[label] = [hashlib.sha256((out_dir / f).read_bytes()).hexdigest() for f in files] + [json.dumps(tf["frames"])]
+    assert digests["one_batch"] == digests["two_views_per_batch"] == digests["one_view_per_batch"]
+    assert len(set(digests["one_batch"][:7])) == 7  # seven different frames
+    # a frame that cannot be written fails the call as a whole (the error of a worker thread is not lost)
+    blocked = tmp_path / "blocked" / "images"
+    blocked.mkdir(parents=True)
+    (blocked / "image_003.png").mkdir()
+    bad = X.XRayRenderer().render({"input": str(scenes / "cube_w_hole.json"), "output_dir": str(blocked), "resolution": 40,
+                                   "num_images": 7, "transforms_file": str(tmp_path / "blocked" / "transforms.json")})
+    assert bad["success"] is False and "render failed" in bad["error"]

@@ -11,6 +11,7 @@
 """
 from __future__ import annotations
 
+import concurrent.futures
 import ctypes
 import json
 import math
@@ -213,6 +214,8 @@ class XRayRenderer:
     """Drop-in for the reference's ``XRayRenderer`` (xray_renderer.py:63): same ``render`` contract,
     backed by the B200 plugin instead of the Go shared library."""
 
+    RENDER_BATCH_BYTES = 1 << 30  # images rendered per library call by render()
+
     def __init__(self, library_path: Optional[str] = None, precision: str = "fp32", devices=None):
         if library_path:
             os.environ["XRAY_CUDA_LIB"] = library_path
@@ -282,9 +285,6 @@ class XRayRenderer:
         R, fov = float(p["R"]), float(p["fov"])
         cams = cameras_from_angles(norm, R, fov)
         integration = "simple" if p["integration"] == "simple" else "hierarchical"  # api.go:128-132
-        imgs = render_scene(scene, cams, res, integration=integration, precision=self.precision, ds=ds,
-                            flat_field=float(p["flat_field"]), density_multiplier=float(p["density_multiplier"]),
-                            devices=self.devices)
         f = 1 / math.tan((fov / 2) * math.pi / 180.0)
         transform_params = {
             "flat_field": math.exp(-float(p["flat_field"])),
@@ -297,9 +297,33 @@ class XRayRenderer:
             "cy": float(res) / 2.0,
             "frames": [],
         }
-        for i_img in range(len(norm)):
-            filename = os.path.join(p["output_dir"], _go_sprintf_int(p["fname_pattern"], i_img))
-            write_png(filename, image_to_rgba8(imgs[i_img], bool(p["transparency"])))
+        # The reference renders and saves one view at a time (main.go:430-522).  Here the views go through the library in
+        # batches of at most RENDER_BATCH_BYTES of images (2880 views at 4096^2 would otherwise be 193 GB of host memory),
+        # and a batch's frames are quantised and PNG-encoded by a few threads (zlib releases the GIL) while the next batch
+        # renders; two batches are alive at most.  File names, frame order and bytes do not depend on the batching.
+        n_views = len(norm)
+        per_view = res * res * (8 if self.precision == "fp64" else 4)
+        batch = max(1, min(n_views, self.RENDER_BATCH_BYTES // max(1, per_view)))
+        transparency = bool(p["transparency"])
+        filenames = [os.path.join(p["output_dir"], _go_sprintf_int(p["fname_pattern"], i_img)) for i_img in range(n_views)]
+
+        def save(filename, img):
+            write_png(filename, image_to_rgba8(img, transparency))
+
+        workers = max(1, min(8, os.cpu_count() or 1, n_views))
+        with concurrent.futures.ThreadPoolExecutor(max_workers=workers) as pool:
+            in_flight = []  # futures of the previous batch
+            for v0 in range(0, n_views, batch):
+                sub = [cams[k] for k in range(v0, min(n_views, v0 + batch))]
+                imgs = render_scene(scene, sub, res, integration=integration, precision=self.precision, ds=ds,
+                                    flat_field=float(p["flat_field"]), density_multiplier=float(p["density_multiplier"]),
+                                    devices=self.devices)
+                for fut in in_flight:
+                    fut.result()  # re-raises a failed write; bounds the images alive to two batches
+                in_flight = [pool.submit(save, filenames[v0 + k], imgs[k]) for k in range(len(sub))]
+            for fut in in_flight:
+                fut.result()
+        for i_img, filename in enumerate(filenames):
             dname, fname = os.path.split(filename)
             rel = os.path.join(os.path.basename(dname), fname)
             transform_params["frames"].append({"file_path": rel.replace(os.sep, "/"), "time": float(p["time_label"]),
