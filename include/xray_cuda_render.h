@@ -116,6 +116,9 @@ typedef struct XRayScene XRayScene; /* opaque: compiled scene (flattened instruc
 /* Thread-local text of the last error returned by any entry point on this thread. */
 const char* XRayLastError(void);
 int XRayDeviceCount(void);
+/* Static text identifying this build: target architecture, nvcc version, compile date and time (so that a run's record
+ * shows which binary it loaded and whether it was compiled on that machine). */
+const char* XRayBuildInfo(void);
 /* Free the per-device scratch (streams, staging buffers, lattice tables) the library keeps between calls. */
 void XRayReleaseCaches(void);
 void XRayRenderOptsInit(XRayRenderOpts* opts);

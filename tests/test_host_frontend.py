@@ -401,3 +401,9 @@ def test_renderer_batches_views_and_threads_the_png_writes(X, scenes, tmp_path, 
     bad = X.XRayRenderer().render({"input": str(scenes / "cube_w_hole.json"), "output_dir": str(blocked), "resolution": 40,
                                    "num_images": 7, "transforms_file": str(tmp_path / "blocked" / "transforms.json")})
     assert bad["success"] is False and "render failed" in bad["error"]
+
+
+def test_build_info_names_the_target_and_the_compiler(X):
+    info = X._lib.library_info()
+    assert "sm_100a" in info["build"] and "nvcc 12." in info["build"] and "DEVELOPMENT" not in info["build"]
+    assert len(info["sha256"]) == 64 and info["bytes"] > 1 << 20 and info["path"].endswith("libcuda_render.so")

@@ -28,7 +28,7 @@ EXTENDED_SYMBOLS = (
     "XRaySceneSetVoxelData", "XRaySceneDensityHost", "XRayCameraFromAngles", "XRayRenderSceneCUDA",
     "XRayRenderSceneDeviceCUDA", "XRayRenderVolumeExCUDA", "XRayRenderVolumeDeviceCUDA", "XRayRenderVolumeDeviceToHostCUDA",
     "XRayVoxelizeSceneCUDA",
-    "XRayMeasureFp32Peak",
+    "XRayMeasureFp32Peak", "XRayBuildInfo",
 )
 
 
@@ -85,6 +85,22 @@ def find_library() -> str:
     return LIB_NAME
 
 
+def library_info() -> dict:
+    """Which binary this process loaded: path, size, modification time, SHA-256 and the build text compiled into it."""
+    import hashlib
+    import time
+
+    L = load()
+    path = find_library()
+    st = os.stat(path)
+    h = hashlib.sha256()
+    with open(path, "rb") as fh:
+        for chunk in iter(lambda: fh.read(1 << 20), b""):
+            h.update(chunk)
+    return {"path": str(path), "bytes": st.st_size, "mtime_utc": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(st.st_mtime)),
+            "sha256": h.hexdigest(), "build": L.XRayBuildInfo().decode()}
+
+
 def load() -> ctypes.CDLL:
     """dlopen the plugin and declare every prototype; raises if it is missing (no fallback)."""
     global _lib
@@ -114,6 +130,7 @@ def load() -> ctypes.CDLL:
     # extended surface
     L.XRayLastError.restype = c_char_p
     L.XRayDeviceCount.restype = c_int
+    L.XRayBuildInfo.restype = c_char_p
     L.XRayRenderOptsInit.argtypes = [ctypes.POINTER(XRayRenderOpts)]
     L.XRaySceneCompileJSON.restype = c_int
     L.XRaySceneCompileJSON.argtypes = [c_char_p, c_char_p, ctypes.POINTER(c_void_p)]

@@ -1286,6 +1286,17 @@ void XRayReleaseCaches(void) {
     cudaSetDevice(cur);
 }
 
+#define XR_STR2(x) #x
+#define XR_STR(x) XR_STR2(x)
+const char* XRayBuildInfo(void) {
+    return "libcuda_render.so (xray_projection_render_b200), sm_100a only, nvcc " XR_STR(__CUDACC_VER_MAJOR__) "." XR_STR(
+        __CUDACC_VER_MINOR__) "." XR_STR(__CUDACC_VER_BUILD__) ", api.cu compiled " __DATE__ " " __TIME__
+#ifdef XRAY_DEV_KNOBS
+           ", DEVELOPMENT build (XRAY_DEV_KNOBS)"
+#endif
+        ;
+}
+
 int XRayDeviceCount(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
