@@ -609,7 +609,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line["configs"] = subs
     if world == 1:
         line["reference_output_pin"] = go_output_pin(X)
-    line["library"] = X._lib.library_info()  # which libcuda_render.so ran, and when / with what it was compiled
+    try:
+        line["library"] = X._lib.library_info()  # which libcuda_render.so ran, and when / with what it was compiled
+    except Exception as e:  # evidence beside the measurement, never a reason to lose the line
+        line["library"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu:
         cb = cpu_baseline(args.workload, budget_s=args.cpu_budget, volume=volume if is_volume else None)
         line["cpu_baseline"] = {"value": cb["gsamples_per_s"], "unit": "Gsamples/s", "cores": cb["cores"], "kind": cb["kind"],
